@@ -1,0 +1,145 @@
+/* rtb200.h -- C ABI of the B200-native ray-tracing hot path (librtb200.so).
+ *
+ * This boundary replaces the OpenCL host<->device seam of the reference
+ * (itmanager85/real-time-opencl-raytracer); each entry point cites what it stands in for.
+ * File names are relative to the reference tree; "vR.cl" = x64/Release/volumeRender.cl.
+ *
+ *   reference call (RayTracer.cpp)                         replacement
+ *   ------------------------------------------------------ ---------------------------
+ *   setupCL(): context, queue, program, kernel :2370-2433   rt_create
+ *   11 x clCreateBuffer(COPY_HOST_PTR)         :942-984     rt_upload_scene
+ *   17 x clSetKernelArg                        :1228-1260   (bound inside the context)
+ *   clEnqueueWriteBuffer(params, 128 B)        :671         rt_set_params
+ *   clEnqueueNDRangeKernel + clFinish +
+ *   clEnqueueReadBuffer(w*h*4)                 :332-343     rt_render_frame
+ *   traverse_bvh(Ray*, tHit, ..., needClosestHit) vR.cl:658 rt_trace  (batch operator)
+ *   ~RayTraceData, cleanup()                   :208-228,1263-1287  rt_destroy
+ *
+ * Conventions: every function returns 0 on success (the reference's SDK_SUCCESS) and a non-zero
+ * RT_E_* code on failure; nothing throws or exits; rt_last_error() gives the text. Host pointers
+ * are borrowed for the duration of the call only. A context is used from one host thread at a
+ * time; different contexts (one per GPU) may be driven concurrently. There is NO CPU fallback:
+ * without a CUDA device rt_create fails with RT_E_NO_DEVICE.
+ *
+ * All scene inputs are in the REFERENCE layouts (no re-packing required from the caller):
+ *   verts          float4[V], w = 1                         Mesh::vertices            (Mesh.h:73)
+ *   indices        int[3T]                                  Mesh::indices             (Mesh.h:72)
+ *   nodes          48 B[N] {float4 min, float4 max, int left, right, tri_off, tri_cnt}
+ *                                                           BVH_Cuda::bvh_nodes       (BVH_Cuda.h:12-29)
+ *   tri_indices    int[R], each = 3 * triangle id           BVH_Cuda::tri_indices     (BVH_Cuda.h:90-93)
+ *   normals        float4[Vn]; normal_indices int[3T]       Mesh::normals(_indices)   (Mesh.h:76-77)
+ *   materials      176 B[M] {int4 technique, 10 x float4}   Mesh::materials           (Mesh.h:20-33)
+ *   tri_to_material int[T]                                  Mesh::triangle_index_to_material_index
+ *   params         8 x float4 {a,b,c,campos,light_pos,light_color,aabb_min,aabb_max}  (RayTracer.cpp:115-161)
+ *
+ * Results are bit-identical to the reference traversal as restated in oracle/oracle.c: same hit
+ * index (3 * triangle id, or -1), same t, and the Moller-Trumbore u,v of the accepted triangle.
+ */
+#ifndef RTB200_H
+#define RTB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rt_context rt_context;
+
+enum {
+    RT_OK = 0,
+    RT_E_INVALID = 1,    /* bad argument / malformed scene */
+    RT_E_NO_DEVICE = 2,  /* no usable CUDA device: there is no CPU fallback */
+    RT_E_CUDA = 3,       /* a CUDA runtime call failed */
+    RT_E_NO_SCENE = 4,   /* trace/render before rt_upload_scene */
+    RT_E_NO_PARAMS = 5   /* render before rt_set_params */
+};
+
+enum { RT_CLOSEST = 0, RT_ANY = 1 }; /* needClosestHit = true / false (vR.cl:659) */
+
+/* (float)UINT_MAX: the reference's initial hit distance (HitRecordInit, vR.cl:223-227) */
+#define RT_T_INIT 4294967296.0f
+
+/* One ray of the batch operator, 32 bytes. `dir` is used exactly as given: the caller normalises
+ * it the way RayInit does (vR.cl:205-211). tmax is the initial *tHit (RT_T_INIT in the reference). */
+typedef struct { float ox, oy, oz, tmax, dx, dy, dz, reserved; } rt_ray;
+/* One result, 16 bytes: idx = 3 * triangle id or -1; t = final *tHit; u,v = barycentrics of the
+ * accepted triangle (weights of its 2nd and 3rd vertex), 0 when idx < 0. */
+typedef struct { int32_t idx; float t, u, v; } rt_hit;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int rt_create(int device_ordinal, rt_context** out_ctx);   /* replaces setupCL() */
+int rt_destroy(rt_context* ctx);                            /* replaces cleanup() + ~RayTraceData */
+const char* rt_last_error(const rt_context* ctx);           /* ctx may be NULL: last rt_create error */
+const char* rt_version(void);
+
+/* Run all work of this context on an existing CUDA stream (a cudaStream_t passed as void*), e.g.
+ * the caller's framework stream so that its events bracket our kernels. NULL = the context's own. */
+int rt_set_stream(rt_context* ctx, void* cuda_stream);
+int rt_synchronize(rt_context* ctx);
+
+/* ---- scene ---------------------------------------------------------------------------------- */
+/* Replaces the clCreateBuffer calls of initRayTrace() (RayTracer.cpp:942-984). normals,
+ * normal_indices, materials, tri_to_material may be NULL (with Vn = M = 0) when only rt_trace /
+ * rt_primary_* are used; rt_render_frame then fails with RT_E_INVALID. The flat BVH is validated
+ * (index ranges, acyclic) and re-packed on the device into 64-byte node pairs + 48-byte
+ * pre-subtracted triangles; see DESIGN.md "Data layout in HBM". */
+int rt_upload_scene(rt_context* ctx, const float* verts, int V, const int32_t* indices, int T, const void* nodes, int N,
+                    const int32_t* tri_indices, int R, const float* normals, int Vn, const int32_t* normal_indices,
+                    const void* materials, int M, const int32_t* tri_to_material);
+
+/* The packed device scene is ONE contiguous, position-independent device allocation so that it can
+ * be broadcast to other GPUs as a single buffer (NCCL) and adopted there without a host round trip. */
+int rt_scene_blob(rt_context* ctx, void** out_device_ptr, size_t* out_bytes);
+/* Adopt a blob that already sits in this device's memory (borrowed: the caller keeps it alive). */
+int rt_adopt_scene_blob(rt_context* ctx, void* device_ptr, size_t bytes);
+
+/* Replaces clEnqueueWriteBuffer(params) in updateCamera() (RayTracer.cpp:671). */
+int rt_set_params(rt_context* ctx, const float params[32]);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* Whole frame = the raytracer_bvh kernel (vR.cl:1043-1547): primary rays, <= 3 path segments of
+ * closest-hit + any-hit shadow + mirror reflection, GGX shading, RGBA8 pack. out_host receives
+ * w*h uint32 pixels, row-major, pixel = (b<<16)|(g<<8)|r as rgbToInt (vR.cl:186-195).
+ * Replaces raytrace_gpgpu() (RayTracer.cpp:330-344). */
+int rt_render_frame(rt_context* ctx, int w, int h, uint32_t* out_host);
+
+/* Batch operator = traverse_bvh (vR.cl:658-1010) on n caller-supplied rays; host buffers. */
+int rt_trace(rt_context* ctx, int mode, int64_t n, const rt_ray* rays_host, rt_hit* hits_host);
+
+/* ---- device-resident variants (benchmarks, multi-GPU plumbing; pointers are device memory) ---- */
+int rt_trace_device(rt_context* ctx, int mode, int64_t n, const rt_ray* d_rays, rt_hit* d_hits);
+/* Primary rays of a w x h frame generated in-kernel from the Params block (vR.cl:1156-1196) and
+ * traced closest-hit; pixel i = y*w+x. Pixels failing the scene-AABB gate get idx = -1,
+ * t = RT_T_INIT. d_rays_out (optional, may be NULL) receives the generated rays. Only rows
+ * y with (y / band_rows) % n_parts == part are produced (part = 0, n_parts = 1: whole frame);
+ * untouched rows are left as they are. */
+int rt_primary_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
+                      rt_ray* d_rays_out);
+/* Shadow rays built in-kernel from rays + their closest hits exactly as vR.cl:1314,1407-1441 and
+ * traced any-hit. Entries whose hit idx < 0 produce idx = -1, t = RT_T_INIT. d_shadow_rays_out may
+ * be NULL. */
+int rt_shadow_device(rt_context* ctx, int64_t n, const rt_ray* d_rays, const rt_hit* d_hits, rt_hit* d_shadow_hits,
+                     rt_ray* d_shadow_rays_out);
+/* Synthetic incoherent workload (not in the reference, BASELINE config 4): `spp` cosine-weighted
+ * hemisphere rays about the geometric normal of every hit, origin = hit point + n * 1e-3, hash RNG
+ * seeded by (ray index * spp + s + seed). Writes rays for valid hits compacted in index order and
+ * the count to *d_count (device int64). */
+int rt_diffuse_rays_device(rt_context* ctx, int64_t n, const rt_ray* d_rays, const rt_hit* d_hits, int spp, uint32_t seed,
+                           rt_ray* d_out_rays, int64_t* d_count);
+/* Frame into a device framebuffer (w*h uint32); band partition as in rt_primary_device. */
+int rt_render_frame_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, uint32_t* d_out);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+enum { RT_CNT_KERNEL_LAUNCHES = 0, RT_CNT_RAYS_TRACED = 1, RT_CNT_H2D_BYTES = 2, RT_CNT_D2H_BYTES = 3, RT_CNT_COUNT = 8 };
+int rt_get_counters(rt_context* ctx, uint64_t out[RT_CNT_COUNT]);
+int rt_reset_counters(rt_context* ctx);
+/* Traversal variant selector for experiments (see DESIGN.md "Kernels"); 0 = default. */
+int rt_set_option(rt_context* ctx, const char* name, int value);
+/* Scene statistics: [0] node pairs, [1] packed triangles, [2] blob bytes, [3] max tree depth */
+int rt_scene_info(rt_context* ctx, int64_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB200_H */

@@ -1,0 +1,339 @@
+// kernels.cuh -- sm_100a kernels around traverse(): ray sources (buffer / camera / shadow), the
+// persistent warp scheduler, the frame megakernel (shading + pack) and the diffuse-ray generator.
+#pragma once
+#include <cstdint>
+
+#include "traverse.cuh"
+
+namespace rtb {
+
+struct ParamsBlock {  // the reference's 128-byte Params (RayTracer.cpp:115-161): 8 x float4, w = 1
+    float4 a, b, c, campos, light_pos, light_color, aabb_min, aabb_max;
+};
+
+struct RayIO {  // rt_ray / rt_hit as two / one 16-byte vectors
+    float4 o_tmax;  // ox oy oz tmax
+    float4 d_pad;   // dx dy dz reserved
+};
+
+enum RaySource { SRC_BUFFER = 0, SRC_PRIMARY = 1, SRC_SHADOW = 2 };
+
+struct TraceArgs {
+    SceneView scene;
+    ParamsBlock params;
+    // work description
+    long long n;              // SRC_BUFFER / SRC_SHADOW: number of rays
+    int w, h;                 // SRC_PRIMARY: frame size
+    int tiles_x;              // SRC_PRIMARY: 8-pixel-wide tiles per row
+    int part, n_parts;        // SRC_PRIMARY: interleaved row bands, this rank's share
+    int band_tile_rows;       // band_rows / 4
+    long long num_batches;    // warp-sized work items
+    // buffers
+    const float4* rays_in;    // SRC_BUFFER, SRC_SHADOW (2 x float4 per ray)
+    const float4* hits_in;    // SRC_SHADOW (closest hits of rays_in)
+    float4* hits_out;         // 1 x float4 per ray {bits(idx), t, u, v}
+    float4* rays_out;         // optional: the generated rays (SRC_PRIMARY, SRC_SHADOW)
+    unsigned int* frame_out;  // render kernel only
+    unsigned long long* work_counter;  // persistent-warp work queue head (zeroed before launch)
+};
+
+static constexpr int kBlockThreads = 128;
+static constexpr int kWarpsPerBlock = kBlockThreads / 32;
+
+// ---- ray sources ---------------------------------------------------------------------------------
+
+// volumeRender.cl:1156-1196: pixel -> primary ray; returns the scene-AABB gate
+__device__ __forceinline__ bool primary_ray(const ParamsBlock& P, unsigned x, unsigned y, unsigned w, unsigned h, Ray& r) {
+    // (x-0.5)/((float)w): exact in fp32 (see oracle/oracle.c primary_ray)
+    const float xf = ((float)x - 0.5f) / ((float)w);
+    const float yf = ((float)y - 0.5f) / ((float)h);
+    const f3 t1 = add3(ld3(P.c), scale3(ld3(P.a), xf));
+    const f3 t2 = scale3(ld3(P.b), yf);
+    const f3 image_pos = add3(t1, t2);
+    r = ray_init(image_pos, sub3(image_pos, ld3(P.campos)));
+    return scene_gate(ld3(P.aabb_min), ld3(P.aabb_max), r);
+}
+
+// volumeRender.cl:1314 + 1407-1441: shadow ray from a path vertex
+__device__ __forceinline__ Ray shadow_ray(f3 light_pos, const Ray& r, float t, f3& hitpoint) {
+    hitpoint = add3(r.ori, scale3(r.dir, (t - 0.001f)));
+    const f3 L = normalize3(sub3(light_pos, hitpoint));
+    return ray_init(add3(hitpoint, scale3(L, 0.001f)), L);
+}
+
+// Map a primary-ray batch (one warp = one 8x4 pixel tile) to pixel coordinates.
+__device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, int lane, int& x, int& y) {
+    const int tx = (int)(batch % a.tiles_x);
+    const long long k = batch / a.tiles_x;  // index among this rank's tile rows
+    const long long band = (long long)a.part + (k / a.band_tile_rows) * a.n_parts;
+    const long long tile_row = band * a.band_tile_rows + (k % a.band_tile_rows);
+    x = tx * 8 + (lane & 7);
+    y = (int)(tile_row * 4 + (lane >> 3));
+}
+
+__device__ __forceinline__ void store_ray(float4* rays_out, long long i, const Ray& r) {
+    rays_out[2 * i] = make_float4(r.ori.x, r.ori.y, r.ori.z, RTB_T_INIT);
+    rays_out[2 * i + 1] = make_float4(r.dir.x, r.dir.y, r.dir.z, 0.0f);
+}
+
+// ---- persistent-warp trace kernel ------------------------------------------------------------------
+// Grid = (resident blocks per SM) x 148 SMs; every warp pulls 32-ray batches from a global queue
+// head with one atomicAdd by lane 0 + a shuffle, until the queue is empty.
+template <int SRC, bool ANY_HIT, bool SMEM_TOP>
+__global__ void __launch_bounds__(kBlockThreads) trace_kernel(const TraceArgs a, int smem_count) {
+    extern __shared__ float4 smem_pairs[];
+    if (SMEM_TOP) {
+        for (int i = threadIdx.x; i < smem_count * 4; i += blockDim.x) smem_pairs[i] = a.scene.pairs[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long batch = 0;
+        if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
+        batch = __shfl_sync(0xffffffffu, batch, 0);
+        if (batch >= (unsigned long long)a.num_batches) break;
+
+        Ray ray;
+        float tmax = RTB_T_INIT;
+        long long out_index = -1;
+        bool active = false;
+        if (SRC == SRC_BUFFER) {
+            const long long i = (long long)batch * 32 + lane;
+            if (i < a.n) {
+                const float4 o = __ldg(a.rays_in + 2 * i), d = __ldg(a.rays_in + 2 * i + 1);
+                ray.ori = ld3(o);
+                ray.dir = ld3(d);
+                tmax = o.w;
+                out_index = i;
+                active = true;
+            }
+        } else if (SRC == SRC_PRIMARY) {
+            int x, y;
+            tile_pixel(a, (long long)batch, lane, x, y);
+            if (x < a.w && y < a.h) {
+                out_index = (long long)y * a.w + x;
+                active = primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray);
+                if (a.rays_out) store_ray(a.rays_out, out_index, ray);
+                if (!active) a.hits_out[out_index] = make_float4(__int_as_float(-1), RTB_T_INIT, 0.0f, 0.0f);
+            }
+        } else {  // SRC_SHADOW
+            const long long i = (long long)batch * 32 + lane;
+            if (i < a.n) {
+                out_index = i;
+                const float4 hin = __ldg(a.hits_in + i);
+                if (__float_as_int(hin.x) >= 0) {
+                    const float4 o = __ldg(a.rays_in + 2 * i), d = __ldg(a.rays_in + 2 * i + 1);
+                    Ray pr;
+                    pr.ori = ld3(o);
+                    pr.dir = ld3(d);
+                    f3 hp;
+                    ray = shadow_ray(ld3(a.params.light_pos), pr, hin.y, hp);
+                    active = true;
+                    if (a.rays_out) store_ray(a.rays_out, i, ray);
+                } else {
+                    a.hits_out[i] = make_float4(__int_as_float(-1), RTB_T_INIT, 0.0f, 0.0f);
+                    if (a.rays_out) {
+                        a.rays_out[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        a.rays_out[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+        }
+        if (active) {
+            const TraceResult r = traverse<ANY_HIT, SMEM_TOP>(a.scene, smem_pairs, smem_count, ray, tmax);
+            a.hits_out[out_index] = make_float4(__int_as_float(r.idx), r.t, r.u, r.v);
+        }
+    }
+}
+
+// ---- frame megakernel: the whole raytracer_bvh kernel (volumeRender.cl:1043-1547) ------------------
+
+#define RTB_PI_F 3.14159274101257f
+#define RTB_RAY_TRACE_DEPTH 3
+
+// volumeRender.cl:27-53
+__device__ __forceinline__ f3 normal_at_tri_point(f3 pNew, f3 p0, f3 p1, f3 p2, f3 vn0, f3 vn1, f3 vn2) {
+    const float Det = p0.x * (p1.y * p2.z - p2.y * p1.z) - p1.x * (p0.y * p2.z - p2.y * p0.z) +
+                      p2.x * (p0.y * p1.z - p1.y * p0.z);
+    const float Det_l0 = pNew.x * (p1.y * p2.z - p2.y * p1.z) - p1.x * (pNew.y * p2.z - p2.y * pNew.z) +
+                         p2.x * (pNew.y * p1.z - p1.y * pNew.z);
+    const float Det_l1 = p0.x * (pNew.y * p2.z - p2.y * pNew.z) - pNew.x * (p0.y * p2.z - p2.y * p0.z) +
+                         p2.x * (p0.y * pNew.z - pNew.y * p0.z);
+    const float Det_l2 = p0.x * (p1.y * pNew.z - pNew.y * p1.z) - p1.x * (p0.y * pNew.z - pNew.y * p0.z) +
+                         pNew.x * (p0.y * p1.z - p1.y * p0.z);
+    const f3 l = mk3(Det_l0 / Det, Det_l1 / Det, Det_l2 / Det);
+    return add3(add3(scale3(vn0, l.x), scale3(vn1, l.y)), scale3(vn2, l.z));
+}
+
+// volumeRender.cl:1732-1738
+__device__ __forceinline__ float ggx_partial_geometry(float cosThetaN, float alpha) {
+    const float cosTheta_sqr = clampf(cosThetaN * cosThetaN, 0.0f, 1.0f);
+    const float tan2 = (1 - cosTheta_sqr) / cosTheta_sqr;
+    return 2 / (1 + sqrtf(1 + alpha * alpha * tan2));
+}
+// volumeRender.cl:1740-1746
+__device__ __forceinline__ float ggx_distribution(float cosThetaNH, float alpha) {
+    const float alpha2 = alpha * alpha;
+    const float NH_sqr = clampf(cosThetaNH * cosThetaNH, 0.0f, 1.0f);
+    const float den = NH_sqr * alpha2 + (1.0f - NH_sqr);
+    return alpha2 / (RTB_PI_F * den * den);
+}
+__device__ __forceinline__ float max0(float v) { return (0.0f < v) ? v : 0.0f; }
+// volumeRender.cl:1754-1779 (FresnelSchlick :1748-1751 inlined)
+__device__ __forceinline__ f3 cook_torrance_ggx(f3 n, f3 l, f3 v, f3 albedo, f3 f0, float roughness) {
+    n = normalize3(n);
+    v = normalize3(v);
+    l = normalize3(l);
+    const f3 h = normalize3(add3(v, l));
+    const float NL = dot3(n, l);
+    if (NL <= 0.0f) return mk3(0.f, 0.f, 0.f);
+    const float NV = dot3(n, v);
+    if (NV <= 0.0f) return mk3(0.f, 0.f, 0.f);
+    const float NH = dot3(n, h);
+    const float HV = dot3(h, v);
+    const float roug_sqr = roughness * roughness;
+    const float G = ggx_partial_geometry(NV, roug_sqr) * ggx_partial_geometry(NL, roug_sqr);
+    const float D = ggx_distribution(NH, roug_sqr);
+    const float p = powf(1.0f - clampf(HV, 0.0f, 1.0f), 5.0f);
+    const f3 F = mk3(f0.x + (1.0f - f0.x) * p, f0.y + (1.0f - f0.y) * p, f0.z + (1.0f - f0.z) * p);
+    const float GD = G * D;
+    const float den = NV + 0.001f;
+    const f3 specK = mk3(GD * F.x * 0.25f / den, GD * F.y * 0.25f / den, GD * F.z * 0.25f / den);
+    const f3 diffK = mk3(clampf(1.0f - F.x, 0.f, 1.f), clampf(1.0f - F.y, 0.f, 1.f), clampf(1.0f - F.z, 0.f, 1.f));
+    return mk3(max0(albedo.x * diffK.x * NL / RTB_PI_F + specK.x), max0(albedo.y * diffK.y * NL / RTB_PI_F + specK.y),
+               max0(albedo.z * diffK.z * NL / RTB_PI_F + specK.z));
+}
+// volumeRender.cl:186-195
+__device__ __forceinline__ unsigned int rgb_to_int(float r, float g, float b) {
+    r = clampf(r, 0.0f, 255.0f);
+    g = clampf(g, 0.0f, 255.0f);
+    b = clampf(b, 0.0f, 255.0f);
+    return ((unsigned int)b << 16) | ((unsigned int)g << 8) | ((unsigned int)r);
+}
+
+template <bool SMEM_TOP>
+__device__ __forceinline__ unsigned int render_pixel(const TraceArgs& a, const float4* smem_pairs, int smem_count, unsigned x,
+                                                     unsigned y) {
+    const SceneView& s = a.scene;
+    const f3 light_pos = ld3(a.params.light_pos);
+    Ray r;
+    bool continue_path = primary_ray(a.params, x, y, (unsigned)a.w, (unsigned)a.h, r);
+    f3 color = mk3(0.f, 0.f, 0.f);
+    int ray_depth = 0;
+    float shadow_coef_sum = 0.0f;
+
+    while (continue_path && ray_depth < RTB_RAY_TRACE_DEPTH) {
+        const TraceResult hit = traverse<false, SMEM_TOP>(s, smem_pairs, smem_count, r, RTB_T_INIT);
+        float shadow_coef = 1.0f;
+        if (hit.idx >= 0) {
+            ray_depth++;
+            const f3 v0 = ld3(__ldg(s.verts + __ldg(s.indices + hit.idx + 0)));
+            const f3 v1 = ld3(__ldg(s.verts + __ldg(s.indices + hit.idx + 1)));
+            const f3 v2 = ld3(__ldg(s.verts + __ldg(s.indices + hit.idx + 2)));
+            const f3 vn0 = ld3(__ldg(s.normals + __ldg(s.normal_indices + hit.idx + 0)));
+            const f3 vn1 = ld3(__ldg(s.normals + __ldg(s.normal_indices + hit.idx + 1)));
+            const f3 vn2 = ld3(__ldg(s.normals + __ldg(s.normal_indices + hit.idx + 2)));
+            f3 vNew;
+            const Ray sray = shadow_ray(light_pos, r, hit.t, vNew);  // vNew = o + d*(t-0.001)
+            f3 normal = normalize3(normal_at_tri_point(vNew, v0, v1, v2, vn0, vn1, vn2));
+            const f3 l1 = normalize3(sub3(light_pos, vNew));
+            const f3 v = normalize3(sub3(r.ori, vNew));
+            const f3 n = normalize3(normal);
+            const f3 diffuse = ld3(__ldg(s.mat_diffuse + __ldg(s.tri_to_material + hit.idx / 3)));
+            const f3 f0 = scale3(mk3(40.f, 40.f, 40.f), (1 / 255.0f));
+            f3 rez_color = scale3(cook_torrance_ggx(n, l1, v, diffuse, f0, 0.5f), 3.0f);
+            rez_color = add3(rez_color, mul3(mk3(0.3f, 0.3f, 0.3f), diffuse));
+            {
+                const TraceResult sh = traverse<true, SMEM_TOP>(s, smem_pairs, smem_count, sray, RTB_T_INIT);
+                if (sh.idx >= 0 && sh.t > 0.025f) shadow_coef = 0.25f;
+            }
+            color = add3(color, rez_color);
+            shadow_coef_sum += shadow_coef;
+            {  // reflect(i, n) = i - 2.0f * n * dot(n, i)
+                const float d = dot3(normal, r.dir);
+                const f3 refl = sub3(r.dir, scale3(scale3(normal, 2.0f), d));
+                r = ray_init(add3(vNew, scale3(refl, 0.001f)), refl);
+            }
+        } else {
+            continue_path = false;
+        }
+    }
+    if (ray_depth >= 1) {
+        color = div3s(color, (float)ray_depth);
+        shadow_coef_sum /= (float)ray_depth;
+        color = scale3(color, shadow_coef_sum);
+    } else {
+        color = mk3(0.f, 0.f, 0.f);
+    }
+    return rgb_to_int(color.x * 255, color.y * 255, color.z * 255);
+}
+
+template <bool SMEM_TOP>
+__global__ void __launch_bounds__(kBlockThreads) render_kernel(const TraceArgs a, int smem_count) {
+    extern __shared__ float4 smem_pairs[];
+    if (SMEM_TOP) {
+        for (int i = threadIdx.x; i < smem_count * 4; i += blockDim.x) smem_pairs[i] = a.scene.pairs[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long batch = 0;
+        if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
+        batch = __shfl_sync(0xffffffffu, batch, 0);
+        if (batch >= (unsigned long long)a.num_batches) break;
+        int x, y;
+        tile_pixel(a, (long long)batch, lane, x, y);
+        if (x < a.w && y < a.h)
+            a.frame_out[(size_t)y * a.w + x] = render_pixel<SMEM_TOP>(a, smem_pairs, smem_count, (unsigned)x, (unsigned)y);
+    }
+}
+
+// ---- synthetic incoherent workload (BASELINE config 4; not part of the reference) -------------------
+
+__device__ __forceinline__ unsigned int lowbias32(unsigned int x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+__global__ void diffuse_flags_kernel(long long n, const float4* hits, int* flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = __float_as_int(hits[i].x) >= 0 ? 1 : 0;
+}
+
+// `spp` cosine-weighted hemisphere directions about the geometric normal (flipped to face the
+// incoming ray), origin = hit point + n * 1e-3; slot = (rank among valid hits) * spp + s.
+__global__ void diffuse_rays_kernel(SceneView s, long long n, const float4* rays, const float4* hits, const int* offsets,
+                                    int spp, unsigned int seed, float4* out_rays, long long* out_count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 h = hits[i];
+    const int idx = __float_as_int(h.x);
+    if (i == n - 1 && out_count) *out_count = ((long long)offsets[i] + (idx >= 0 ? 1 : 0)) * spp;
+    if (idx < 0) return;
+    const f3 o = ld3(rays[2 * i]), d = ld3(rays[2 * i + 1]);
+    const f3 p0 = ld3(s.verts[s.indices[idx]]), p1 = ld3(s.verts[s.indices[idx + 1]]), p2 = ld3(s.verts[s.indices[idx + 2]]);
+    f3 nrm = normalize3(cross3(sub3(p1, p0), sub3(p2, p0)));
+    if (dot3(nrm, d) > 0.0f) nrm = mk3(-nrm.x, -nrm.y, -nrm.z);
+    const f3 hp = add3(o, scale3(d, h.y));
+    const f3 org = add3(hp, scale3(nrm, 1e-3f));
+    // orthonormal basis (Duff et al. 2017)
+    const float sg = copysignf(1.0f, nrm.z);
+    const float aa = -1.0f / (sg + nrm.z);
+    const float bb = nrm.x * nrm.y * aa;
+    const f3 t1 = mk3(1.0f + sg * nrm.x * nrm.x * aa, sg * bb, -sg * nrm.x);
+    const f3 t2 = mk3(bb, sg + nrm.y * nrm.y * aa, -nrm.y);
+    for (int k = 0; k < spp; k++) {
+        const unsigned int h1 = lowbias32((unsigned int)(i * spp + k) + seed);
+        const unsigned int h2 = lowbias32(h1 ^ 0x9e3779b9u);
+        const float u1 = (float)(h1 >> 8) * (1.0f / 16777216.0f);
+        const float u2 = (float)(h2 >> 8) * (1.0f / 16777216.0f);
+        const float rr = sqrtf(u1), phi = 6.283185307179586f * u2;
+        const float lx = rr * cosf(phi), ly = rr * sinf(phi), lz = sqrtf(fmaxf(0.0f, 1.0f - u1));
+        const f3 dir = normalize3(add3(add3(scale3(t1, lx), scale3(t2, ly)), scale3(nrm, lz)));
+        const long long slot = (long long)offsets[i] * spp + k;
+        out_rays[2 * slot] = make_float4(org.x, org.y, org.z, RTB_T_INIT);
+        out_rays[2 * slot + 1] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+    }
+}
+
+}  // namespace rtb

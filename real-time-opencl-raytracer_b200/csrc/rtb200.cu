@@ -1,0 +1,465 @@
+// rtb200.cu -- the extern "C" boundary of include/rtb200.h over the sm_100a kernels.
+// Replaces the OpenCL context/queue/kernel plumbing of the reference (RayTracer.cpp:93-109,
+// 858-1005, 1222-1287, 2050-2433). No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/rtb200.h"
+
+#include <cub/device/device_scan.cuh>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "kernels.cuh"
+#include "scene_blob.h"
+
+using namespace rtb;
+
+static_assert(sizeof(rt_ray) == 32 && sizeof(rt_hit) == 16, "ABI record sizes");
+
+struct rt_context {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    // scene
+    uint8_t* d_blob = nullptr;
+    size_t blob_bytes = 0;
+    bool blob_owned = false;
+    BlobHeader hdr;
+    SceneView view;
+    bool have_scene = false;
+    // params
+    ParamsBlock params;
+    bool have_params = false;
+    // scratch
+    unsigned long long* d_counter = nullptr;
+    void* d_stage_in = nullptr;
+    size_t stage_in_bytes = 0;
+    void* d_stage_out = nullptr;
+    size_t stage_out_bytes = 0;
+    void* d_scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+    int* d_flags = nullptr;
+    int* d_offsets = nullptr;
+    size_t flags_count = 0;
+    // options
+    int opt_smem_top = 0;     // number of top pairs staged in shared memory (0 = off)
+    int opt_blocks_per_sm = 0;  // 0 = occupancy-derived
+    int opt_top_pairs = 2047;   // BFS-ordered prefix chosen at pack time
+    uint64_t counters[RT_CNT_COUNT] = {0};
+    std::string err;
+};
+
+static std::string g_create_error;
+
+static int set_err(rt_context* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CK(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return set_err(ctx, RT_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* rt_version(void) { return "rtb200 0.1 (sm_100a)"; }
+
+extern "C" const char* rt_last_error(const rt_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int rt_create(int device_ordinal, rt_context** out_ctx) {
+    if (!out_ctx) return set_err(nullptr, RT_E_INVALID, "rt_create: out_ctx is NULL");
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_err(nullptr, RT_E_NO_DEVICE, "rt_create: no CUDA device (%s); this library has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device_ordinal < 0 || device_ordinal >= count)
+        return set_err(nullptr, RT_E_INVALID, "rt_create: device %d out of range [0,%d)", device_ordinal, count);
+    rt_context* ctx = new rt_context();
+    ctx->device = device_ordinal;
+    CK(nullptr, cudaSetDevice(device_ordinal));
+    cudaDeviceProp prop;
+    CK(nullptr, cudaGetDeviceProperties(&prop, device_ordinal));
+    ctx->num_sms = prop.multiProcessorCount;
+    CK(nullptr, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    CK(nullptr, cudaMalloc(&ctx->d_counter, 256));
+    memset(&ctx->hdr, 0, sizeof ctx->hdr);
+    memset(&ctx->view, 0, sizeof ctx->view);
+    *out_ctx = ctx;
+    return RT_OK;
+}
+
+static void free_scene(rt_context* ctx) {
+    if (ctx->d_blob && ctx->blob_owned) cudaFree(ctx->d_blob);
+    ctx->d_blob = nullptr;
+    ctx->blob_bytes = 0;
+    ctx->blob_owned = false;
+    ctx->have_scene = false;
+}
+
+extern "C" int rt_destroy(rt_context* ctx) {
+    if (!ctx) return RT_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    cudaFree(ctx->d_counter);
+    cudaFree(ctx->d_stage_in);
+    cudaFree(ctx->d_stage_out);
+    cudaFree(ctx->d_scan_tmp);
+    cudaFree(ctx->d_flags);
+    cudaFree(ctx->d_offsets);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return RT_OK;
+}
+
+extern "C" int rt_set_stream(rt_context* ctx, void* cuda_stream) {
+    if (!ctx) return RT_E_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return RT_OK;
+}
+
+extern "C" int rt_synchronize(rt_context* ctx) {
+    if (!ctx) return RT_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+static int bind_blob(rt_context* ctx, const BlobHeader& h, uint8_t* d_blob, size_t bytes, bool owned) {
+    if (h.magic != kBlobMagic || h.version != kBlobVersion || h.total_bytes != bytes)
+        return set_err(ctx, RT_E_INVALID, "scene blob header mismatch (magic %08x version %u bytes %llu vs %zu)", h.magic,
+                       h.version, (unsigned long long)h.total_bytes, bytes);
+    free_scene(ctx);
+    ctx->d_blob = d_blob;
+    ctx->blob_bytes = bytes;
+    ctx->blob_owned = owned;
+    ctx->hdr = h;
+    SceneView& v = ctx->view;
+    v.pairs = (const float4*)(d_blob + h.off_pairs);
+    v.tris = (const float4*)(d_blob + h.off_tris);
+    v.verts = (const float4*)(d_blob + h.off_verts);
+    v.indices = (const int*)(d_blob + h.off_indices);
+    v.normals = (const float4*)(d_blob + h.off_normals);
+    v.normal_indices = (const int*)(d_blob + h.off_normal_indices);
+    v.mat_diffuse = (const float4*)(d_blob + h.off_mat_diffuse);
+    v.tri_to_material = (const int*)(d_blob + h.off_tri_to_material);
+    v.root_ref = h.root_ref;
+    v.num_pairs = h.num_pairs;
+    v.top_pairs = h.top_pairs;
+    ctx->have_scene = true;
+    return RT_OK;
+}
+
+extern "C" int rt_upload_scene(rt_context* ctx, const float* verts, int V, const int32_t* indices, int T, const void* nodes,
+                               int N, const int32_t* tri_indices, int R, const float* normals, int Vn,
+                               const int32_t* normal_indices, const void* materials, int M, const int32_t* tri_to_material) {
+    if (!ctx) return RT_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    SceneInputs in = {verts, V, indices, T, nodes, N, tri_indices, R, normals, Vn, normal_indices, materials, M, tri_to_material};
+    uint8_t* blob = nullptr;
+    uint64_t bytes = 0;
+    char err[256] = {0};
+    if (pack_scene(in, ctx->opt_top_pairs, &blob, &bytes, err, sizeof err)) return set_err(ctx, RT_E_INVALID, "%s", err);
+    uint8_t* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, blob, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    BlobHeader h;
+    memcpy(&h, blob, sizeof h);
+    free(blob);
+    if (e != cudaSuccess) {
+        if (d) cudaFree(d);
+        return set_err(ctx, RT_E_CUDA, "rt_upload_scene: uploading %llu bytes failed: %s", (unsigned long long)bytes,
+                       cudaGetErrorString(e));
+    }
+    ctx->counters[RT_CNT_H2D_BYTES] += bytes;
+    return bind_blob(ctx, h, d, bytes, true);
+}
+
+extern "C" int rt_scene_blob(rt_context* ctx, void** out_device_ptr, size_t* out_bytes) {
+    if (!ctx || !out_device_ptr || !out_bytes) return RT_E_INVALID;
+    if (!ctx->have_scene) return set_err(ctx, RT_E_NO_SCENE, "rt_scene_blob: no scene uploaded");
+    *out_device_ptr = ctx->d_blob;
+    *out_bytes = ctx->blob_bytes;
+    return RT_OK;
+}
+
+extern "C" int rt_adopt_scene_blob(rt_context* ctx, void* device_ptr, size_t bytes) {
+    if (!ctx || !device_ptr || bytes < sizeof(BlobHeader)) return RT_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    BlobHeader h;
+    CK(ctx, cudaMemcpyAsync(&h, device_ptr, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return bind_blob(ctx, h, (uint8_t*)device_ptr, bytes, false);
+}
+
+extern "C" int rt_set_params(rt_context* ctx, const float params[32]) {
+    if (!ctx || !params) return RT_E_INVALID;
+    memcpy(&ctx->params, params, sizeof(ParamsBlock));
+    ctx->have_params = true;
+    return RT_OK;
+}
+
+extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
+    if (!ctx || !name) return RT_E_INVALID;
+    if (!strcmp(name, "smem_top")) ctx->opt_smem_top = value < 0 ? 0 : value;
+    else if (!strcmp(name, "blocks_per_sm")) ctx->opt_blocks_per_sm = value < 0 ? 0 : value;
+    else if (!strcmp(name, "top_pairs")) ctx->opt_top_pairs = value < 0 ? 0 : value;  // takes effect at the next upload
+    else return set_err(ctx, RT_E_INVALID, "rt_set_option: unknown option '%s'", name);
+    return RT_OK;
+}
+
+extern "C" int rt_scene_info(rt_context* ctx, int64_t out[4]) {
+    if (!ctx || !out) return RT_E_INVALID;
+    if (!ctx->have_scene) return set_err(ctx, RT_E_NO_SCENE, "rt_scene_info: no scene uploaded");
+    out[0] = ctx->hdr.num_pairs;
+    out[1] = ctx->hdr.num_tris;
+    out[2] = (int64_t)ctx->blob_bytes;
+    out[3] = ctx->hdr.max_depth;
+    return RT_OK;
+}
+
+extern "C" int rt_get_counters(rt_context* ctx, uint64_t out[RT_CNT_COUNT]) {
+    if (!ctx || !out) return RT_E_INVALID;
+    memcpy(out, ctx->counters, sizeof ctx->counters);
+    return RT_OK;
+}
+extern "C" int rt_reset_counters(rt_context* ctx) {
+    if (!ctx) return RT_E_INVALID;
+    memset(ctx->counters, 0, sizeof ctx->counters);
+    return RT_OK;
+}
+
+// ---- launch helpers ------------------------------------------------------------------------------
+
+template <typename K>
+static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, int smem_count) {
+    const size_t smem = (size_t)smem_count * 64;
+    if (smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = ctx->opt_blocks_per_sm;
+    if (per_sm <= 0) {
+        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, smem));
+        if (per_sm < 1) per_sm = 1;
+    }
+    long long blocks = (long long)per_sm * ctx->num_sms;
+    const long long needed = (a.num_batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > needed) blocks = needed;
+    if (blocks < 1) return RT_OK;  // nothing to do
+    a.work_counter = ctx->d_counter;
+    CK(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
+    kernel<<<(unsigned)blocks, kBlockThreads, smem, ctx->stream>>>(a, smem_count);
+    CK(ctx, cudaGetLastError());
+    ctx->counters[RT_CNT_KERNEL_LAUNCHES]++;
+    return RT_OK;
+}
+
+static int smem_top_count(const rt_context* ctx) {
+    int c = ctx->opt_smem_top;
+    if (c > ctx->hdr.top_pairs) c = ctx->hdr.top_pairs;
+    if (c > 3400) c = 3400;  // 3400 * 64 B = 217.6 KB < 227 KB
+    return c;
+}
+
+static int require(rt_context* ctx, bool params, bool shading) {
+    if (!ctx) return RT_E_INVALID;
+    if (!ctx->have_scene) return set_err(ctx, RT_E_NO_SCENE, "no scene uploaded (rt_upload_scene / rt_adopt_scene_blob)");
+    if (params && !ctx->have_params) return set_err(ctx, RT_E_NO_PARAMS, "no params set (rt_set_params)");
+    if (shading && (ctx->hdr.Vn == 0 || ctx->hdr.M == 0))
+        return set_err(ctx, RT_E_INVALID, "scene was uploaded without normals/materials: shading is unavailable");
+    return RT_OK;
+}
+
+static int band_setup(rt_context* ctx, TraceArgs& a, int w, int h, int part, int n_parts, int band_rows) {
+    if (w <= 0 || h <= 0 || n_parts < 1 || part < 0 || part >= n_parts || band_rows < 4 || (band_rows % 4))
+        return set_err(ctx, RT_E_INVALID, "bad frame/band arguments (w=%d h=%d part=%d/%d band_rows=%d; band_rows must be a multiple of 4)",
+                       w, h, part, n_parts, band_rows);
+    a.w = w;
+    a.h = h;
+    a.tiles_x = (w + 7) / 8;
+    a.part = part;
+    a.n_parts = n_parts;
+    a.band_tile_rows = band_rows / 4;
+    const long long bands = ((long long)h + band_rows - 1) / band_rows;
+    const long long owned = bands > part ? (bands - part + n_parts - 1) / n_parts : 0;
+    a.num_batches = owned * a.band_tile_rows * a.tiles_x;
+    return RT_OK;
+}
+
+static int do_trace_device(rt_context* ctx, int mode, long long n, const rt_ray* d_rays, rt_hit* d_hits) {
+    TraceArgs a;
+    memset(&a, 0, sizeof a);
+    a.scene = ctx->view;
+    a.n = n;
+    a.num_batches = (n + 31) / 32;
+    a.rays_in = (const float4*)d_rays;
+    a.hits_out = (float4*)d_hits;
+    const int st = smem_top_count(ctx);
+    int rc;
+    if (mode == RT_CLOSEST)
+        rc = st ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, true>, a, st)
+                : launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false>, a, 0);
+    else
+        rc = st ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, true>, a, st)
+                : launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, false>, a, 0);
+    if (rc == RT_OK) ctx->counters[RT_CNT_RAYS_TRACED] += (uint64_t)n;
+    return rc;
+}
+
+extern "C" int rt_trace_device(rt_context* ctx, int mode, int64_t n, const rt_ray* d_rays, rt_hit* d_hits) {
+    int rc = require(ctx, false, false);
+    if (rc) return rc;
+    if ((mode != RT_CLOSEST && mode != RT_ANY) || n < 0 || (n > 0 && (!d_rays || !d_hits)))
+        return set_err(ctx, RT_E_INVALID, "rt_trace_device: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return RT_OK;
+    return do_trace_device(ctx, mode, n, d_rays, d_hits);
+}
+
+static int ensure(rt_context* ctx, void** p, size_t* have, size_t need) {
+    if (*have >= need) return RT_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    CK(ctx, cudaMalloc(p, need));
+    *have = need;
+    return RT_OK;
+}
+
+extern "C" int rt_trace(rt_context* ctx, int mode, int64_t n, const rt_ray* rays_host, rt_hit* hits_host) {
+    int rc = require(ctx, false, false);
+    if (rc) return rc;
+    if ((mode != RT_CLOSEST && mode != RT_ANY) || n < 0 || (n > 0 && (!rays_host || !hits_host)))
+        return set_err(ctx, RT_E_INVALID, "rt_trace: bad arguments");
+    if (n == 0) return RT_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if ((rc = ensure(ctx, &ctx->d_stage_in, &ctx->stage_in_bytes, (size_t)n * sizeof(rt_ray)))) return rc;
+    if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, (size_t)n * sizeof(rt_hit)))) return rc;
+    CK(ctx, cudaMemcpyAsync(ctx->d_stage_in, rays_host, (size_t)n * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = do_trace_device(ctx, mode, n, (const rt_ray*)ctx->d_stage_in, (rt_hit*)ctx->d_stage_out))) return rc;
+    CK(ctx, cudaMemcpyAsync(hits_host, ctx->d_stage_out, (size_t)n * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->counters[RT_CNT_H2D_BYTES] += (uint64_t)n * sizeof(rt_ray);
+    ctx->counters[RT_CNT_D2H_BYTES] += (uint64_t)n * sizeof(rt_hit);
+    return RT_OK;
+}
+
+extern "C" int rt_primary_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
+                                 rt_ray* d_rays_out) {
+    int rc = require(ctx, true, false);
+    if (rc) return rc;
+    if (!d_hits) return set_err(ctx, RT_E_INVALID, "rt_primary_device: d_hits is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    TraceArgs a;
+    memset(&a, 0, sizeof a);
+    a.scene = ctx->view;
+    a.params = ctx->params;
+    if ((rc = band_setup(ctx, a, w, h, part, n_parts, band_rows))) return rc;
+    a.hits_out = (float4*)d_hits;
+    a.rays_out = (float4*)d_rays_out;
+    const int st = smem_top_count(ctx);
+    rc = st ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, true>, a, st)
+            : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0);
+    if (rc == RT_OK) ctx->counters[RT_CNT_RAYS_TRACED] += (uint64_t)a.num_batches * 32;
+    return rc;
+}
+
+extern "C" int rt_shadow_device(rt_context* ctx, int64_t n, const rt_ray* d_rays, const rt_hit* d_hits, rt_hit* d_shadow_hits,
+                                rt_ray* d_shadow_rays_out) {
+    int rc = require(ctx, true, false);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_rays || !d_hits || !d_shadow_hits))) return set_err(ctx, RT_E_INVALID, "rt_shadow_device: bad arguments");
+    if (n == 0) return RT_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    TraceArgs a;
+    memset(&a, 0, sizeof a);
+    a.scene = ctx->view;
+    a.params = ctx->params;
+    a.n = n;
+    a.num_batches = (n + 31) / 32;
+    a.rays_in = (const float4*)d_rays;
+    a.hits_in = (const float4*)d_hits;
+    a.hits_out = (float4*)d_shadow_hits;
+    a.rays_out = (float4*)d_shadow_rays_out;
+    const int st = smem_top_count(ctx);
+    rc = st ? launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, true>, a, st)
+            : launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, false>, a, 0);
+    if (rc == RT_OK) ctx->counters[RT_CNT_RAYS_TRACED] += (uint64_t)n;
+    return rc;
+}
+
+extern "C" int rt_diffuse_rays_device(rt_context* ctx, int64_t n, const rt_ray* d_rays, const rt_hit* d_hits, int spp,
+                                      uint32_t seed, rt_ray* d_out_rays, int64_t* d_count) {
+    int rc = require(ctx, false, false);
+    if (rc) return rc;
+    if (n <= 0 || n > 0x7fffffff || !d_rays || !d_hits || spp < 1 || !d_out_rays)
+        return set_err(ctx, RT_E_INVALID, "rt_diffuse_rays_device: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->flags_count < (size_t)n) {
+        cudaFree(ctx->d_flags);
+        cudaFree(ctx->d_offsets);
+        ctx->d_flags = ctx->d_offsets = nullptr;
+        ctx->flags_count = 0;
+        CK(ctx, cudaMalloc(&ctx->d_flags, (size_t)n * 4));
+        CK(ctx, cudaMalloc(&ctx->d_offsets, (size_t)n * 4));
+        ctx->flags_count = (size_t)n;
+    }
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    diffuse_flags_kernel<<<blocks, threads, 0, ctx->stream>>>(n, (const float4*)d_hits, ctx->d_flags);
+    CK(ctx, cudaGetLastError());
+    size_t tmp = 0;
+    CK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->d_flags, ctx->d_offsets, (int)n, ctx->stream));
+    if ((rc = ensure(ctx, &ctx->d_scan_tmp, &ctx->scan_tmp_bytes, tmp ? tmp : 1))) return rc;
+    CK(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_scan_tmp, tmp, ctx->d_flags, ctx->d_offsets, (int)n, ctx->stream));
+    diffuse_rays_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->view, n, (const float4*)d_rays, (const float4*)d_hits,
+                                                             ctx->d_offsets, spp, seed, (float4*)d_out_rays,
+                                                             (long long*)d_count);
+    CK(ctx, cudaGetLastError());
+    ctx->counters[RT_CNT_KERNEL_LAUNCHES] += 2;
+    return RT_OK;
+}
+
+extern "C" int rt_render_frame_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, uint32_t* d_out) {
+    int rc = require(ctx, true, true);
+    if (rc) return rc;
+    if (!d_out) return set_err(ctx, RT_E_INVALID, "rt_render_frame_device: d_out is NULL");
+    CK(ctx, cudaSetDevice(ctx->device));
+    TraceArgs a;
+    memset(&a, 0, sizeof a);
+    a.scene = ctx->view;
+    a.params = ctx->params;
+    if ((rc = band_setup(ctx, a, w, h, part, n_parts, band_rows))) return rc;
+    a.frame_out = d_out;
+    const int st = smem_top_count(ctx);
+    rc = st ? launch_persistent(ctx, render_kernel<true>, a, st) : launch_persistent(ctx, render_kernel<false>, a, 0);
+    return rc;
+}
+
+extern "C" int rt_render_frame(rt_context* ctx, int w, int h, uint32_t* out_host) {
+    int rc = require(ctx, true, true);
+    if (rc) return rc;
+    if (!out_host || w <= 0 || h <= 0) return set_err(ctx, RT_E_INVALID, "rt_render_frame: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)w * h * 4;
+    if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, bytes))) return rc;
+    if ((rc = rt_render_frame_device(ctx, w, h, 0, 1, 4, (uint32_t*)ctx->d_stage_out))) return rc;
+    CK(ctx, cudaMemcpyAsync(out_host, ctx->d_stage_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->counters[RT_CNT_H2D_BYTES] += sizeof(ParamsBlock);
+    ctx->counters[RT_CNT_D2H_BYTES] += bytes;
+    return RT_OK;
+}

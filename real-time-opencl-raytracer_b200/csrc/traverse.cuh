@@ -1,0 +1,111 @@
+// traverse.cuh -- the hot loop: stack-based BVH traversal + ray/triangle tests (closest / any hit).
+//
+// Semantics = the reference's traverse_bvh (x64/Release/volumeRender.cl:658-1010; restated in
+// oracle/oracle.c traverse_bvh), on the packed layout of scene_blob.h:
+//   * same binary tree, same child order, same box arithmetic (true division), same three-way
+//     intersect test `tmin<=tmax && tmax>=TMIN && tmin<=tHit` (vR.cl:866-867)
+//   * both children hit: the one with the smaller entry distance first, LEFT on ties (vR.cl:903);
+//     the far child goes on the stack. Stack overflow (65 entries incl. the current node) and
+//     malformed nodes return -1 and discard an already found hit (vR.cl:841,855-856,914)
+//   * leaf triangles in stored order, accept iff `t < tHit && t > TMIN` (strict, vR.cl:978);
+//     any-hit returns the FIRST accepted triangle (vR.cl:986) -- the shadow rule thresholds that
+//     triangle's t, so the visiting order is part of the contract
+// What differs is only where the bytes come from: one 64-byte node pair (4 x LDG.128) per inner
+// visit instead of 3 dependent loads from 3 nodes, one 48-byte pre-subtracted triangle
+// (3 x LDG.128) per test instead of ref -> 3 indices -> 3 vertices.
+//
+// Loop shape: while-while (an inner-node loop and a leaf loop inside one outer loop), the current
+// node held in a register and only the postponed nodes in the per-thread stack.
+#pragma once
+#include "device_math.cuh"
+#include "scene_blob.h"
+
+namespace rtb {
+
+struct SceneView {
+    const float4* pairs;
+    const float4* tris;
+    const float4* verts;
+    const int* indices;
+    const float4* normals;
+    const int* normal_indices;
+    const float4* mat_diffuse;
+    const int* tri_to_material;
+    int root_ref;
+    int num_pairs;
+    int top_pairs;
+};
+
+struct TraceResult {
+    int idx;
+    float t, u, v;
+};
+
+// Node fetch policy: TOP > 0 means pairs [0, TOP) are served from shared memory (`smem_pairs`).
+template <bool ANY_HIT, bool SMEM_TOP>
+__device__ __forceinline__ TraceResult traverse(const SceneView& s, const float4* __restrict__ smem_pairs, int smem_count,
+                                                const Ray& ray, float tHit) {
+    int stack[RTB_STACK];
+    int sp = 0;
+    int cur = s.root_ref;
+    TraceResult res;
+    res.idx = -1;
+    res.u = 0.0f;
+    res.v = 0.0f;
+
+    for (;;) {
+        // ---- inner nodes ------------------------------------------------------------------
+        while (cur >= 0) {
+            float4 q0, q1, q2, q3;
+            if (SMEM_TOP && cur < smem_count) {
+                const float4* p = smem_pairs + 4 * cur;
+                q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3];
+            } else {
+                const float4* p = s.pairs + 4 * (size_t)cur;
+                q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
+            }
+            float t0n, t0f, t1n, t1f;
+            ray_box(ray, q0, q1, t0n, t0f);
+            ray_box(ray, q2, q3, t1n, t1f);
+            const bool hit0 = (t0n <= t0f) && (t0f >= RTB_TMIN) && (t0n <= tHit);
+            const bool hit1 = (t1n <= t1f) && (t1f >= RTB_TMIN) && (t1n <= tHit);
+            int c0 = __float_as_int(q0.w), c1 = __float_as_int(q2.w);
+            if (hit0 && hit1) {
+                if (t0n > t1n) { const int t = c0; c0 = c1; c1 = t; }
+                if (sp >= RTB_STACK) { res.idx = -1; res.t = tHit; res.u = res.v = 0.0f; return res; }
+                stack[sp++] = c1;
+                cur = c0;
+            } else if (hit0) {
+                cur = c0;
+            } else if (hit1) {
+                cur = c1;
+            } else {
+                if (sp == 0) { res.t = tHit; return res; }
+                cur = stack[--sp];
+            }
+        }
+        // ---- leaf --------------------------------------------------------------------------
+        if (cur == kRefPoison) { res.idx = -1; res.t = tHit; res.u = res.v = 0.0f; return res; }
+        {
+            const float4* tp = s.tris + 3 * (size_t)(~cur);
+            for (;;) {
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                float u, v;
+                const float t = ray_triangle(ray, ld3(a), ld3(b), ld3(c), u, v);
+                if (t < tHit && t > RTB_TMIN) {
+                    tHit = t;
+                    res.idx = __float_as_int(a.w);
+                    res.u = u;
+                    res.v = v;
+                    if (ANY_HIT) { res.t = tHit; return res; }
+                }
+                if (__float_as_int(b.w) != 0) break;
+                tp += 3;
+            }
+        }
+        if (sp == 0) { res.t = tHit; return res; }
+        cur = stack[--sp];
+    }
+}
+
+}  // namespace rtb

@@ -1,0 +1,183 @@
+"""ctypes binding of the C ABI in include/rtb200.h (librtb200.so, hand-written sm_100a CUDA).
+
+There is no CPU fallback: if the library is missing, or no CUDA device is present, the calls raise.
+Host-side mirror of the reference's launch seam (reference RayTracer.cpp: setupCL :2370,
+initRayTrace :858, updateCamera :609, raytrace_gpgpu :330, cleanup :1263)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librtb200.so")
+_lib = None
+
+CLOSEST, ANY = 0, 1
+T_INIT = np.float32(4294967296.0)
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("tmax", np.float32), ("d", np.float32, 3), ("reserved", np.float32)])
+HIT_DTYPE = np.dtype([("idx", np.int32), ("t", np.float32), ("u", np.float32), ("v", np.float32)])
+
+ABI_SYMBOLS = [
+    "rt_create", "rt_destroy", "rt_last_error", "rt_version", "rt_set_stream", "rt_synchronize", "rt_upload_scene",
+    "rt_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_trace_device",
+    "rt_primary_device", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
+    "rt_reset_counters", "rt_set_option", "rt_scene_info",
+]
+
+
+class RtError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RtError(f"{LIB_PATH} is missing (build it with __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+        L.rt_create.argtypes = [i32, C.POINTER(vp)]
+        L.rt_destroy.argtypes = [vp]
+        L.rt_last_error.argtypes = [vp]
+        L.rt_last_error.restype = C.c_char_p
+        L.rt_version.restype = C.c_char_p
+        L.rt_set_stream.argtypes = [vp, vp]
+        L.rt_synchronize.argtypes = [vp]
+        L.rt_upload_scene.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp]
+        L.rt_scene_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.rt_adopt_scene_blob.argtypes = [vp, vp, C.c_size_t]
+        L.rt_set_params.argtypes = [vp, vp]
+        L.rt_render_frame.argtypes = [vp, i32, i32, vp]
+        L.rt_trace.argtypes = [vp, i32, i64, vp, vp]
+        L.rt_trace_device.argtypes = [vp, i32, i64, vp, vp]
+        L.rt_primary_device.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
+        L.rt_shadow_device.argtypes = [vp, i64, vp, vp, vp, vp]
+        L.rt_diffuse_rays_device.argtypes = [vp, i64, vp, vp, i32, C.c_uint32, vp, vp]
+        L.rt_render_frame_device.argtypes = [vp, i32, i32, i32, i32, i32, vp]
+        L.rt_get_counters.argtypes = [vp, vp]
+        L.rt_reset_counters.argtypes = [vp]
+        L.rt_set_option.argtypes = [vp, C.c_char_p, i32]
+        L.rt_scene_info.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    """numpy array -> host pointer; torch tensor / int -> device pointer; None -> NULL"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if isinstance(a, int):
+        return a
+    return a.data_ptr()
+
+
+class Context:
+    """One `rt_context` = one GPU. Mirrors the reference's global CL state + RayTraceData."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().rt_create(device, C.byref(self._h))
+        if rc:
+            raise RtError(f"rt_create({device}) failed [{rc}]: {lib().rt_last_error(None).decode()}")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise RtError(f"[{rc}] {lib().rt_last_error(self._h).decode()}")
+
+    # --- plumbing ---
+    def set_stream(self, cuda_stream_handle):
+        self._ck(lib().rt_set_stream(self._h, cuda_stream_handle))
+
+    def synchronize(self):
+        self._ck(lib().rt_synchronize(self._h))
+
+    def set_option(self, name, value):
+        self._ck(lib().rt_set_option(self._h, name.encode(), int(value)))
+
+    def counters(self):
+        out = np.zeros(8, dtype=np.uint64)
+        self._ck(lib().rt_get_counters(self._h, out.ctypes.data))
+        return {"kernel_launches": int(out[0]), "rays_traced": int(out[1]), "h2d_bytes": int(out[2]), "d2h_bytes": int(out[3])}
+
+    def reset_counters(self):
+        self._ck(lib().rt_reset_counters(self._h))
+
+    def scene_info(self):
+        out = np.zeros(4, dtype=np.int64)
+        self._ck(lib().rt_scene_info(self._h, out.ctypes.data))
+        return {"node_pairs": int(out[0]), "packed_tris": int(out[1]), "blob_bytes": int(out[2]), "max_depth": int(out[3])}
+
+    # --- scene (reference initRayTrace buffers) ---
+    def upload_scene(self, mesh, bvh_nodes, tri_indices, shading=True):
+        """mesh: dict from hostlib.Mesh.arrays(); bvh_nodes (N,12) f32 words; tri_indices (R,) i32."""
+        c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        verts, indices = c(mesh["verts"], np.float32), c(mesh["indices"], np.int32)
+        nodes, tri = c(bvh_nodes, np.float32), c(tri_indices, np.int32)
+        use_shading = shading and len(mesh.get("normals", ())) > 0 and len(mesh.get("materials", ())) > 0
+        if use_shading:
+            normals, nidx = c(mesh["normals"], np.float32), c(mesh["normal_indices"], np.int32)
+            mats, t2m = c(mesh["materials"], np.float32), c(mesh["tri_to_material"], np.int32)
+            Vn, M = normals.shape[0], mats.shape[0]
+        else:
+            normals = nidx = mats = t2m = None
+            Vn = M = 0
+        self._ck(lib().rt_upload_scene(self._h, _ptr(verts), verts.shape[0], _ptr(indices), indices.size // 3, _ptr(nodes),
+                                       nodes.shape[0], _ptr(tri), tri.size, _ptr(normals), Vn, _ptr(nidx), _ptr(mats), M,
+                                       _ptr(t2m)))
+
+    def scene_blob(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(lib().rt_scene_blob(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def adopt_scene_blob(self, device_ptr, nbytes):
+        self._ck(lib().rt_adopt_scene_blob(self._h, device_ptr, nbytes))
+
+    def set_params(self, params32):
+        p = np.ascontiguousarray(params32, dtype=np.float32)
+        assert p.size == 32
+        self._ck(lib().rt_set_params(self._h, p.ctypes.data))
+
+    # --- hot path, host buffers ---
+    def render_frame(self, w, h, out=None):
+        if out is None:
+            out = np.empty((h, w), dtype=np.uint32)
+        self._ck(lib().rt_render_frame(self._h, w, h, _ptr(out)))
+        return out
+
+    def trace(self, mode, rays, hits=None):
+        n = rays.shape[0] if isinstance(rays, np.ndarray) else rays.numel() * rays.element_size() // 32
+        if hits is None:
+            hits = np.empty(n, dtype=HIT_DTYPE)
+        self._ck(lib().rt_trace(self._h, mode, n, _ptr(rays), _ptr(hits)))
+        return hits
+
+    # --- hot path, device buffers (torch tensors or raw device pointers) ---
+    def trace_device(self, mode, n, d_rays, d_hits):
+        self._ck(lib().rt_trace_device(self._h, mode, n, _ptr(d_rays), _ptr(d_hits)))
+
+    def primary_device(self, w, h, d_hits, d_rays_out=None, part=0, n_parts=1, band_rows=4):
+        self._ck(lib().rt_primary_device(self._h, w, h, part, n_parts, band_rows, _ptr(d_hits), _ptr(d_rays_out)))
+
+    def shadow_device(self, n, d_rays, d_hits, d_shadow_hits, d_shadow_rays_out=None):
+        self._ck(lib().rt_shadow_device(self._h, n, _ptr(d_rays), _ptr(d_hits), _ptr(d_shadow_hits), _ptr(d_shadow_rays_out)))
+
+    def diffuse_rays_device(self, n, d_rays, d_hits, spp, seed, d_out_rays, d_count):
+        self._ck(lib().rt_diffuse_rays_device(self._h, n, _ptr(d_rays), _ptr(d_hits), spp, seed, _ptr(d_out_rays), _ptr(d_count)))
+
+    def render_frame_device(self, w, h, d_out, part=0, n_parts=1, band_rows=4):
+        self._ck(lib().rt_render_frame_device(self._h, w, h, part, n_parts, band_rows, _ptr(d_out)))
