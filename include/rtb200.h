@@ -82,7 +82,7 @@ int rt_synchronize(rt_context* ctx);
 /* Replaces the clCreateBuffer calls of initRayTrace() (RayTracer.cpp:942-984). normals,
  * normal_indices, materials, tri_to_material may be NULL (with Vn = M = 0) when only rt_trace /
  * rt_primary_* are used; rt_render_frame then fails with RT_E_INVALID. The flat BVH is validated
- * (index ranges, acyclic) and re-packed on the device into 64-byte node pairs + 48-byte
+ * (index ranges, acyclic) and re-packed (once, on the host) into 64-byte node pairs + 48-byte
  * pre-subtracted triangles; see DESIGN.md "Data layout in HBM". */
 int rt_upload_scene(rt_context* ctx, const float* verts, int V, const int32_t* indices, int T, const void* nodes, int N,
                     const int32_t* tri_indices, int R, const float* normals, int Vn, const int32_t* normal_indices,
@@ -106,6 +106,12 @@ int rt_render_frame(rt_context* ctx, int w, int h, uint32_t* out_host);
 
 /* Batch operator = traverse_bvh (vR.cl:658-1010) on n caller-supplied rays; host buffers. */
 int rt_trace(rt_context* ctx, int mode, int64_t n, const rt_ray* rays_host, rt_hit* hits_host);
+
+/* Primary-ray pass of a w x h frame with the current Params (vR.cl:1156-1196 + the first
+ * traverse_bvh call of vR.cl:1238): hits_host receives w*h records, pixel i = y*w+x. Pixels that
+ * fail the scene-AABB gate get idx = -1, t = RT_T_INIT. Host buffer out; the device->host copy of
+ * finished row bands overlaps the tracing of the next ones. */
+int rt_primary(rt_context* ctx, int w, int h, rt_hit* hits_host);
 
 /* ---- device-resident variants (benchmarks, multi-GPU plumbing; pointers are device memory) ---- */
 int rt_trace_device(rt_context* ctx, int mode, int64_t n, const rt_ray* d_rays, rt_hit* d_hits);

@@ -24,6 +24,8 @@ struct rt_context {
     int num_sms = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // device->host copies that overlap tracing (rt_primary)
+    cudaEvent_t chunk_events[16] = {nullptr};
     // scene
     uint8_t* d_blob = nullptr;
     size_t blob_bytes = 0;
@@ -95,6 +97,8 @@ extern "C" int rt_create(int device_ordinal, rt_context** out_ctx) {
     ctx->num_sms = prop.multiProcessorCount;
     CK(nullptr, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    CK(nullptr, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : ctx->chunk_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CK(nullptr, cudaMalloc(&ctx->d_counter, 256));
     memset(&ctx->hdr, 0, sizeof ctx->hdr);
     memset(&ctx->view, 0, sizeof ctx->view);
@@ -121,6 +125,9 @@ extern "C" int rt_destroy(rt_context* ctx) {
     cudaFree(ctx->d_scan_tmp);
     cudaFree(ctx->d_flags);
     cudaFree(ctx->d_offsets);
+    for (auto& ev : ctx->chunk_events)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return RT_OK;
@@ -375,6 +382,34 @@ extern "C" int rt_primary_device(rt_context* ctx, int w, int h, int part, int n_
             : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0);
     if (rc == RT_OK) ctx->counters[RT_CNT_RAYS_TRACED] += (uint64_t)a.num_batches * 32;
     return rc;
+}
+
+// Host-buffer primary pass: the frame is cut into up to 8 contiguous row chunks; chunk c is traced on
+// the context stream while chunk c-1 is copied to the host on the copy stream.
+extern "C" int rt_primary(rt_context* ctx, int w, int h, rt_hit* hits_host) {
+    int rc = require(ctx, true, false);
+    if (rc) return rc;
+    if (!hits_host || w <= 0 || h <= 0) return set_err(ctx, RT_E_INVALID, "rt_primary: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)w * h * sizeof(rt_hit);
+    if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, bytes))) return rc;
+    int chunks = 8;
+    int rows = (((h + chunks - 1) / chunks) + 3) & ~3;  // rows per chunk, multiple of the 4-row warp tile
+    chunks = (h + rows - 1) / rows;
+    for (int c = 0; c < chunks; c++) {
+        if ((rc = rt_primary_device(ctx, w, h, c, chunks, rows, (rt_hit*)ctx->d_stage_out, nullptr))) return rc;
+        CK(ctx, cudaEventRecord(ctx->chunk_events[c], ctx->stream));
+        CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_events[c], 0));
+        const int y0 = c * rows, y1 = (y0 + rows < h) ? y0 + rows : h;
+        const size_t off = (size_t)y0 * w * sizeof(rt_hit), len = (size_t)(y1 - y0) * w * sizeof(rt_hit);
+        CK(ctx, cudaMemcpyAsync((uint8_t*)hits_host + off, (uint8_t*)ctx->d_stage_out + off, len, cudaMemcpyDeviceToHost,
+                                ctx->copy_stream));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->counters[RT_CNT_H2D_BYTES] += sizeof(ParamsBlock);
+    ctx->counters[RT_CNT_D2H_BYTES] += bytes;
+    return RT_OK;
 }
 
 extern "C" int rt_shadow_device(rt_context* ctx, int64_t n, const rt_ray* d_rays, const rt_hit* d_hits, rt_hit* d_shadow_hits,

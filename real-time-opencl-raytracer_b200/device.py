@@ -19,7 +19,7 @@ HIT_DTYPE = np.dtype([("idx", np.int32), ("t", np.float32), ("u", np.float32), (
 
 ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_version", "rt_set_stream", "rt_synchronize", "rt_upload_scene",
-    "rt_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_trace_device",
+    "rt_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_primary", "rt_trace_device",
     "rt_primary_device", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
     "rt_reset_counters", "rt_set_option", "rt_scene_info",
 ]
@@ -50,6 +50,7 @@ def lib():
         L.rt_render_frame.argtypes = [vp, i32, i32, vp]
         L.rt_trace.argtypes = [vp, i32, i64, vp, vp]
         L.rt_trace_device.argtypes = [vp, i32, i64, vp, vp]
+        L.rt_primary.argtypes = [vp, i32, i32, vp]
         L.rt_primary_device.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
         L.rt_shadow_device.argtypes = [vp, i64, vp, vp, vp, vp]
         L.rt_diffuse_rays_device.argtypes = [vp, i64, vp, vp, i32, C.c_uint32, vp, vp]
@@ -100,7 +101,13 @@ class Context:
 
     # --- plumbing ---
     def set_stream(self, cuda_stream_handle):
-        self._ck(lib().rt_set_stream(self._h, cuda_stream_handle))
+        """Run on an existing CUDA stream. Handle 0 (the legacy default stream, e.g. torch's default
+        current stream) is passed as cudaStreamLegacy (0x1); None restores the context's own stream."""
+        if cuda_stream_handle is None:
+            handle = None
+        else:
+            handle = 1 if int(cuda_stream_handle) == 0 else int(cuda_stream_handle)
+        self._ck(lib().rt_set_stream(self._h, handle))
 
     def synchronize(self):
         self._ck(lib().rt_synchronize(self._h))
@@ -164,6 +171,13 @@ class Context:
         if hits is None:
             hits = np.empty(n, dtype=HIT_DTYPE)
         self._ck(lib().rt_trace(self._h, mode, n, _ptr(rays), _ptr(hits)))
+        return hits
+
+    def primary(self, w, h, hits=None):
+        """primary-ray pass, host buffer out (numpy array or pinned torch tensor of w*h 16-byte records)"""
+        if hits is None:
+            hits = np.empty(w * h, dtype=HIT_DTYPE)
+        self._ck(lib().rt_primary(self._h, w, h, _ptr(hits)))
         return hits
 
     # --- hot path, device buffers (torch tensors or raw device pointers) ---

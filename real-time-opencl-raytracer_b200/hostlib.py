@@ -117,6 +117,7 @@ class Mesh:
             "tri_to_material": _view(ptrs[5], (T if M else 0,), np.int32),
             "aabb_min": np.array(aabb[0:3], dtype=np.float32),
             "aabb_max": np.array(aabb[3:6], dtype=np.float32),
+            "_owner": self,  # the views alias this Mesh's C++ vectors: keep it alive with the dict
         }
 
 

@@ -1,0 +1,302 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the committed
+golden fixtures. Bar: bit-exact hit index, t, u, v (integer/index work AND the fp32 results, because the
+kernels keep the reference's operation order with FMA contraction off); frames within +-1 LSB (powf)."""
+import numpy as np
+import pytest
+from conftest import SCENES, assert_hits_identical, channel_diff, load_scene, mesh_dict, same_bits
+
+import rtb200
+from oracle import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+HIT = rtb200.HIT_DTYPE
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = rtb200.Context(0)
+    yield c
+    c.close()
+
+
+def _upload(ctx, g):
+    ctx.upload_scene(mesh_dict(g), g["ref_nodes"], g["ref_tri_indices"])
+    ctx.set_params(g["params"])
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_trace_host_buffers_vs_golden(ctx, name):
+    """rt_trace (host rays in, host hits out) == committed oracle outputs on reference-built trees"""
+    g = load_scene(name)
+    _upload(ctx, g)
+    got = ctx.trace(rtb200.CLOSEST, g["primary_rays"])
+    want = g["primary_hits"].view(HIT).reshape(-1)
+    # rt_trace traces every ray it is given; the golden primary hits are ungated too
+    assert_hits_identical(got, want, f"{name} primary closest")
+    assert_hits_identical(ctx.trace(rtb200.CLOSEST, g["random_rays"]), g["random_hits_closest"].view(HIT).reshape(-1), f"{name} random closest")
+    assert_hits_identical(ctx.trace(rtb200.ANY, g["random_rays"]), g["random_hits_any"].view(HIT).reshape(-1), f"{name} random any")
+    v = g["shadow_valid"].astype(bool)
+    if v.any():
+        assert_hits_identical(ctx.trace(rtb200.ANY, g["shadow_rays"][v]), g["shadow_hits"].view(HIT).reshape(-1)[v], f"{name} shadow any")
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_fused_primary_and_shadow_kernels_vs_golden(ctx, name):
+    """in-kernel ray generation (camera, shadow) is bit-identical to the oracle's, gate included"""
+    import torch
+
+    g = load_scene(name)
+    _upload(ctx, g)
+    w, h = (int(v) for v in g["wh"])
+    n = w * h
+    d_hits = torch.full((n, 4), -7.0, device="cuda")
+    d_rays = torch.zeros((n, 8), device="cuda")
+    ctx.primary_device(w, h, d_hits, d_rays)
+    ctx.synchronize()
+    assert same_bits(d_rays.cpu().numpy(), g["primary_rays"])
+    want = g["primary_hits"].view(HIT).reshape(-1).copy()
+    gate = g["primary_gate"].astype(bool)
+    want[~gate] = (-1, rtb200.T_INIT, 0, 0)  # the kernel does not traverse rays that fail the scene-AABB gate
+    got = d_hits.cpu().numpy().view(HIT).reshape(-1)
+    assert_hits_identical(got, want, f"{name} fused primary")
+
+    d_sh = torch.zeros((n, 4), device="cuda")
+    d_sr = torch.zeros((n, 8), device="cuda")
+    ctx.shadow_device(n, d_rays, d_hits, d_sh, d_sr)
+    ctx.synchronize()
+    v = g["shadow_valid"].astype(bool) & gate
+    assert same_bits(d_sr.cpu().numpy()[v], g["shadow_rays"][v])
+    assert_hits_identical(d_sh.cpu().numpy().view(HIT).reshape(-1)[v], g["shadow_hits"].view(HIT).reshape(-1)[v], f"{name} fused shadow")
+    miss = ~(want["idx"] >= 0)
+    assert np.all(d_sh.cpu().numpy().view(HIT).reshape(-1)["idx"][miss] == -1)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_render_frame_vs_golden(ctx, name):
+    g = load_scene(name)
+    _upload(ctx, g)
+    w, h = (int(v) for v in g["wh"])
+    img = ctx.render_frame(w, h)
+    d = channel_diff(img, g["frame"])
+    assert d.max() <= 1, f"{name}: frame differs by {d.max()} LSB on {(d.max(axis=-1) > 1).sum()} pixels"
+    assert (d.max(axis=-1) > 0).mean() < 0.02
+    assert np.all(img >> 24 == 0)
+
+
+@pytest.mark.parametrize("smem_top", [0, 63, 500])
+def test_smem_top_variant_is_identical(ctx, smem_top):
+    g = load_scene("mix")
+    _upload(ctx, g)
+    ctx.set_option("smem_top", smem_top)
+    try:
+        assert_hits_identical(ctx.trace(rtb200.CLOSEST, g["random_rays"]), g["random_hits_closest"].view(HIT).reshape(-1), "closest")
+        assert_hits_identical(ctx.trace(rtb200.ANY, g["random_rays"]), g["random_hits_any"].view(HIT).reshape(-1), "any")
+    finally:
+        ctx.set_option("smem_top", 0)
+
+
+def _medium_scene():
+    m = rtb200.Mesh().terrain(160, 100.0).icosphere(4, 25.0, (20.0, 30.0, -10.0)).sticks(400, 5, 150.0).finish(diffuse=(0.6, 0.7, 0.8))
+    return m, m.arrays(), rtb200.FlatBVH.build(m)
+
+
+def test_medium_scene_all_ray_classes_vs_oracle(ctx):
+    """~56 K triangles with duplicated references, 320x240: primary, grazing-light shadow (order-dependent
+    any-hit), device-generated diffuse rays, and the frame -- all against the live oracle."""
+    import torch
+
+    m, A, b = _medium_scene()
+    assert b.duplicates > 0
+    w, h = 320, 240
+    params, _ = rtb200.camera_params(w, h, A["aabb_min"], A["aabb_max"], light_pos=(-150.0, 25.0, 3.0))
+    ctx.upload_scene(A, b.nodes, b.tri_indices)
+    ctx.set_params(params)
+    sc = O.OracleScene(A, b.nodes, b.tri_indices)
+    rays, gate = O.primary_rays(params, w, h)
+    want, _ = sc.trace(0, rays)
+    got = ctx.trace(rtb200.CLOSEST, rays)
+    assert_hits_identical(got, want, "primary")
+    srays, valid = O.shadow_rays(params, rays, want)
+    v = valid.astype(bool)
+    want_s, _ = sc.trace(1, srays[v])
+    assert 0.05 < (want_s["idx"] >= 0).mean() < 0.95  # the grazing light really occludes some
+    assert_hits_identical(ctx.trace(rtb200.ANY, srays[v]), want_s, "shadow any-hit")
+
+    n = w * h
+    d_rays = torch.from_numpy(rays).cuda()
+    d_hits = torch.from_numpy(want.view(np.float32).reshape(-1, 4).copy()).cuda()
+    d_out = torch.zeros((n * 4, 8), device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ctx.diffuse_rays_device(n, d_rays, d_hits, 4, 0x5EED, d_out, d_cnt)
+    ctx.synchronize()
+    nd = int(d_cnt.item())
+    assert nd == 4 * int((want["idx"] >= 0).sum())
+    drays = d_out[:nd].cpu().numpy()
+    assert np.allclose(np.linalg.norm(drays[:, 4:7], axis=1), 1.0, atol=1e-5)
+    want_d, _ = sc.trace(0, drays)
+    assert_hits_identical(ctx.trace(rtb200.CLOSEST, drays), want_d, "diffuse")
+
+    img = ctx.render_frame(w, h)
+    ref_img, _ = sc.render_frame(params, w, h)
+    d = channel_diff(img, ref_img)
+    assert d.max() <= 1 and (d.max(axis=-1) > 0).mean() < 0.02
+
+
+def test_band_partition_covers_frame(ctx):
+    """interleaved row bands (the multi-GPU partition) of the fused primary + frame kernels tile the frame exactly"""
+    import torch
+
+    g = load_scene("terrain12")
+    _upload(ctx, g)
+    w, h = 96, 64
+    whole = torch.zeros((w * h, 4), device="cuda")
+    ctx.primary_device(w, h, whole)
+    img_whole = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    ctx.render_frame_device(w, h, img_whole)
+    for n_parts, band in ((2, 16), (3, 8), (4, 4)):
+        acc = torch.full((w * h, 4), float("nan"), device="cuda")
+        img = torch.full((h, w), -1, dtype=torch.int32, device="cuda")
+        for part in range(n_parts):
+            ctx.primary_device(w, h, acc, None, part=part, n_parts=n_parts, band_rows=band)
+            ctx.render_frame_device(w, h, img, part=part, n_parts=n_parts, band_rows=band)
+        ctx.synchronize()
+        assert same_bits(acc.cpu().numpy(), whole.cpu().numpy())
+        assert torch.equal(img, img_whole)
+
+
+def test_ragged_and_edge_inputs(ctx):
+    g = load_scene("ico2")
+    _upload(ctx, g)
+    # empty batch
+    assert ctx.trace(rtb200.CLOSEST, np.zeros((0, 8), dtype=np.float32)).size == 0
+    # ragged sizes around the warp width
+    want = g["random_hits_closest"].view(HIT).reshape(-1)
+    for n in (1, 31, 32, 33, 1000):
+        assert_hits_identical(ctx.trace(rtb200.CLOSEST, g["random_rays"][:n].copy()), want[:n], f"n={n}")
+    # frame sizes that are not multiples of the 8x4 warp tile
+    sc = O.OracleScene(mesh_dict(g), g["ref_nodes"], g["ref_tri_indices"])
+    for w, h in ((37, 21), (8, 4), (1, 1)):
+        params, _ = rtb200.camera_params(w, h, g["aabb_min"], g["aabb_max"])
+        ctx.set_params(params)
+        ref_img, _ = sc.render_frame(params, w, h)
+        assert channel_diff(ctx.render_frame(w, h), ref_img).max() <= 1
+    # zero direction components (division by zero in ray_box -> inf/NaN handled like the oracle)
+    rays = np.zeros((64, 8), dtype=np.float32)
+    rays[:, 0:3] = np.random.default_rng(3).normal(size=(64, 3)) * 20
+    rays[:, 3] = rtb200.T_INIT
+    rays[:32, 4] = 1.0   # +x axis-aligned
+    rays[32:, 5] = -1.0  # -y axis-aligned
+    want, _ = sc.trace(0, rays)
+    assert_hits_identical(ctx.trace(rtb200.CLOSEST, rays), want, "axis-aligned rays")
+
+
+def test_root_leaf_scene(ctx):
+    """test0 flattens to a single leaf node (root is a leaf): traversal starts in the leaf loop"""
+    g = load_scene("test0")
+    assert g["ref_nodes"].shape[0] == 1
+    _upload(ctx, g)
+    assert_hits_identical(ctx.trace(rtb200.CLOSEST, g["random_rays"]), g["random_hits_closest"].view(HIT).reshape(-1), "root leaf")
+
+
+def test_error_behaviour(ctx):
+    c2 = rtb200.Context(0)
+    with pytest.raises(rtb200.RtError):  # no scene yet
+        c2.trace(rtb200.CLOSEST, np.zeros((4, 8), dtype=np.float32))
+    g = load_scene("ico2")
+    bad = g["ref_nodes"].copy()
+    bad.view(np.int32)[0, 9] = 10 ** 6  # root's right child out of range -> reference returns -1 for every ray
+    c2.upload_scene(mesh_dict(g), bad, g["ref_tri_indices"])
+    sc = O.OracleScene(mesh_dict(g), bad, g["ref_tri_indices"])
+    want, _ = sc.trace(0, g["random_rays"])
+    assert np.all(want["idx"] == -1)
+    assert_hits_identical(c2.trace(rtb200.CLOSEST, g["random_rays"]), want, "poisoned root")
+    cyc = g["ref_nodes"].copy()
+    cyc.view(np.int32)[1, 8:10] = (0, 0) if cyc.view(np.int32)[1, 8] >= 0 else cyc.view(np.int32)[1, 8:10]
+    if cyc.view(np.int32)[1, 8] == 0:
+        with pytest.raises(rtb200.RtError, match="reachable twice"):
+            c2.upload_scene(mesh_dict(g), cyc, g["ref_tri_indices"])
+    idx = g["indices"].copy()
+    idx[5] = 10 ** 7
+    md = mesh_dict(g)
+    md["indices"] = idx
+    with pytest.raises(rtb200.RtError, match="outside"):
+        c2.upload_scene(md, g["ref_nodes"], g["ref_tri_indices"])
+    with pytest.raises(rtb200.RtError):  # no params
+        c3 = rtb200.Context(0)
+        c3.upload_scene(mesh_dict(g), g["ref_nodes"], g["ref_tri_indices"])
+        c3.render_frame(8, 8)
+    c2.close()
+
+
+def test_scene_blob_adopt_roundtrip(ctx):
+    """the packed scene is one position-independent device buffer: copy it (as NCCL would) and adopt it"""
+    import torch
+
+    g = load_scene("mix")
+    _upload(ctx, g)
+    ptr, nbytes = ctx.scene_blob()
+    src = torch.empty(0, dtype=torch.uint8, device="cuda")
+    import ctypes as C
+
+    clone = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    cudart = torch.cuda.cudart()
+    assert int(cudart.cudaMemcpy(clone.data_ptr(), ptr, nbytes, 3)) == 0  # cudaMemcpyDeviceToDevice
+    c2 = rtb200.Context(0)
+    c2.adopt_scene_blob(clone.data_ptr(), nbytes)
+    assert_hits_identical(c2.trace(rtb200.ANY, g["random_rays"]), g["random_hits_any"].view(HIT).reshape(-1), "adopted blob")
+    c2.close()
+    del src, C
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config 2 at full size (1920x1080, ~1M-triangle terrain): size-independent properties.
+    (a) a 1/64 subsample of the pixels is bit-identical to the oracle; (b) closest t <= any-hit t on the same
+    rays and the occlusion booleans agree; (c) tracing with tmax = t_closest + ulp returns the same hit, with
+    tmax = t_closest returns a different/no hit (strict '<'); (d) re-running is idempotent (bitwise)."""
+    import torch
+
+    m = rtb200.Mesh().terrain(707, 100.0).finish()
+    A = m.arrays()
+    b = rtb200.FlatBVH.build(m)
+    w, h = 1920, 1080
+    params, _ = rtb200.camera_params(w, h, A["aabb_min"], A["aabb_max"])
+    ctx.upload_scene(A, b.nodes, b.tri_indices)
+    ctx.set_params(params)
+    n = w * h
+    d_hits = torch.zeros((n, 4), device="cuda")
+    d_rays = torch.zeros((n, 8), device="cuda")
+    ctx.primary_device(w, h, d_hits, d_rays)
+    ctx.synchronize()
+    hits = d_hits.cpu().numpy().view(HIT).reshape(-1)
+    rays = d_rays.cpu().numpy()
+    assert 0.30 < (hits["idx"] >= 0).mean() < 0.40
+    d_hits2 = torch.zeros((n, 4), device="cuda")
+    ctx.primary_device(w, h, d_hits2)
+    ctx.synchronize()
+    assert torch.equal(d_hits.view(torch.int32), d_hits2.view(torch.int32))  # (d)
+
+    sc = O.OracleScene(A, b.nodes, b.tri_indices)
+    sub = np.arange(0, n, 64)
+    orays, gate = O.primary_rays(params, w, h)
+    assert same_bits(orays[sub], rays[sub])
+    want, _ = sc.trace(0, orays[sub])
+    want[gate[sub] == 0] = (-1, rtb200.T_INIT, 0, 0)
+    assert_hits_identical(hits[sub], want, "1/64 subsample")  # (a)
+
+    d_any = torch.zeros((n, 4), device="cuda")
+    ctx.trace_device(rtb200.ANY, n, d_rays, d_any)
+    ctx.synchronize()
+    anyh = d_any.cpu().numpy().view(HIT).reshape(-1)
+    g = gate.astype(bool)
+    assert np.array_equal(anyh["idx"][g] >= 0, hits["idx"][g] >= 0)  # (b)
+    hit = g & (hits["idx"] >= 0)
+    assert np.all(anyh["t"][hit] >= hits["t"][hit])
+
+    sel = np.flatnonzero(hit)[::97]
+    r2 = rays[sel].copy()
+    r2[:, 3] = np.nextafter(hits["t"][sel], np.float32(np.inf))
+    h2 = ctx.trace(rtb200.CLOSEST, r2)
+    assert np.array_equal(h2["idx"], hits["idx"][sel]) and same_bits(h2["t"], hits["t"][sel])  # (c)
+    r2[:, 3] = hits["t"][sel]
+    h3 = ctx.trace(rtb200.CLOSEST, r2)
+    assert np.all((h3["idx"] != hits["idx"][sel]) | (h3["t"] < hits["t"][sel]))

@@ -1,0 +1,112 @@
+"""Host scene layer: the SBVH builder / flattener must emit byte-identical arrays to the reference's
+own SplitBVHBuilder + BVH_Cuda (golden fixtures made with oracle/_ref/ref_host; live where available)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+from conftest import SCENES, load_scene, same_bits
+
+import rtb200
+from oracle import oracle_py as O
+
+
+def _build(g, threshold=16384):
+    m = rtb200.Mesh().set(g["verts"], g["indices"])
+    return rtb200.FlatBVH.build(m, threshold)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_builder_matches_reference_golden(name):
+    g = load_scene(name)
+    b = _build(g)
+    assert b.num_nodes == g["ref_nodes"].shape[0] and b.num_refs == g["ref_tri_indices"].size
+    assert same_bits(b.nodes, g["ref_nodes"])
+    assert np.array_equal(b.tri_indices, g["ref_tri_indices"])
+
+
+@pytest.mark.parametrize("threshold", [0, 64, 1000])
+def test_parallel_build_is_deterministic(threshold):
+    """task-parallel subtree builds splice back into the serial (reference) emission order"""
+    m = rtb200.Mesh().icosphere(4, 50.0).terrain(40, 100.0).sticks(300, 11, 120.0)
+    a = rtb200.FlatBVH.build(m, 0)
+    b = rtb200.FlatBVH.build(m, threshold)
+    assert same_bits(a.nodes, b.nodes) and np.array_equal(a.tri_indices, b.tri_indices)
+    assert a.duplicates == b.duplicates and a.duplicates > 0  # spatial splits did happen
+
+
+def _ref_build(A, td):
+    payload = np.array([A["verts"].shape[0], A["indices"].size // 3], dtype=np.int32).tobytes() + \
+        np.ascontiguousarray(A["verts"], dtype=np.float32).tobytes() + np.ascontiguousarray(A["indices"], dtype=np.int32).tobytes()
+    out = O.ref_host("build", payload, td)
+    N, R = np.frombuffer(out[:8], dtype=np.int32)
+    return np.frombuffer(out[8:8 + 48 * N], dtype=np.float32).reshape(N, 12), np.frombuffer(out[8 + 48 * N:], dtype=np.int32)
+
+
+@pytest.mark.skipif(not O.ref_host_available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("maker", [
+    lambda: rtb200.Mesh().icosphere(4, 50.0),
+    lambda: rtb200.Mesh().terrain(64, 100.0),
+    lambda: rtb200.Mesh().sticks(2500, 21, 100.0),
+    lambda: rtb200.Mesh().icosphere(3, 40.0, (5.0, 0.0, 0.0)).icosphere(3, 40.0, (-5.0, 3.0, 1.0)).sticks(500, 2, 90.0),
+])
+def test_builder_matches_reference_live(maker):
+    m = maker()
+    A = m.arrays()
+    b = rtb200.FlatBVH.build(m)
+    with tempfile.TemporaryDirectory() as td:
+        nodes, tri = _ref_build(A, td)
+    assert same_bits(b.nodes, nodes) and np.array_equal(b.tri_indices, tri)
+
+
+def test_flat_layout_invariants():
+    """48-byte nodes, pre-order (left child = index+1), w = 1, leaves -1/-1, refs pre-multiplied by 3"""
+    m = rtb200.Mesh().terrain(30, 100.0)
+    b = rtb200.FlatBVH.build(m)
+    ints = b.nodes.view(np.int32)
+    left, right, off, cnt = ints[:, 8], ints[:, 9], ints[:, 10], ints[:, 11]
+    inner = left >= 0
+    assert np.all(left[inner] == np.flatnonzero(inner) + 1)
+    assert np.all(right[inner] > left[inner]) and np.all(off[inner] == -1) and np.all(cnt[inner] == 0)
+    assert np.all(right[~inner] == -1) and np.all(cnt[~inner] >= 1) and np.all(cnt[~inner] <= 8)
+    assert np.all(b.nodes[:, 3] == 1.0) and np.all(b.nodes[:, 7] == 1.0)
+    assert np.all(b.tri_indices % 3 == 0) and cnt[~inner].sum() == b.num_refs
+    # every triangle is referenced at least once
+    assert np.unique(b.tri_indices // 3).size == m.arrays()["indices"].size // 3
+
+
+def test_flat_bvh_disk_cache_roundtrip(tmp_path):
+    m = rtb200.Mesh().icosphere(3, 10.0)
+    b = rtb200.FlatBVH.build(m)
+    p = str(tmp_path / "x.fbvh")
+    b.save(p)
+    c = rtb200.FlatBVH.load(p)
+    assert same_bits(b.nodes, c.nodes) and np.array_equal(b.tri_indices, c.tri_indices)
+
+
+def test_camera_default_pose_and_params():
+    """reference Camera(): radius 200, alpha 225 deg, beta 45 deg -> eye ~ (-100, 141.42, -100) (Camera.cpp:6-19)"""
+    params, eye = rtb200.camera_params(640, 480, (-1, -2, -3), (4, 5, 6))
+    assert np.allclose(eye, [-100.0, 141.42136, -100.0], atol=1e-3)
+    p = params.reshape(8, 4)
+    assert np.all(p[:, 3] == 1.0)
+    a, b, c, campos = p[0, :3], p[1, :3], p[2, :3], p[3, :3]
+    half = np.tan(np.float32(60.0 * 3.1415 * 0.5 / 180.0))
+    assert np.isclose(np.linalg.norm(a), 2 * half * 640 / 480, rtol=1e-5) and np.isclose(np.linalg.norm(b), 2 * half, rtol=1e-5)
+    assert abs(np.dot(a, b)) < 1e-4
+    centre = c + 0.5 * a + 0.5 * b  # image-plane centre = eye + dir
+    assert np.isclose(np.linalg.norm(centre - campos), 1.0, atol=1e-5)
+    assert np.allclose(p[4, :3], [-23, 200, 3]) and np.allclose(p[6, :3], [-1, -2, -3]) and np.allclose(p[7, :3], [4, 5, 6])
+
+
+def test_collada_roundtrip(tmp_path):
+    """generated .dae -> ColladaLoader -> Mesh::init reproduces the mesh exactly (BASELINE config 1 path)"""
+    m = rtb200.Mesh().icosphere(2, 50.0).finish(diffuse=(0.25, 0.5, 0.75))
+    A = m.arrays()
+    p = str(tmp_path / "s.dae")
+    m.write_dae(p)
+    B = rtb200.Mesh().load_dae(p).arrays()
+    for k in ("verts", "indices", "normals", "normal_indices", "tri_to_material"):
+        assert same_bits(A[k], B[k]), k
+    assert np.allclose(A["materials"][0, 12:15], B["materials"][0, 12:15])
+    assert same_bits(A["aabb_min"], B["aabb_min"]) and same_bits(A["aabb_max"], B["aabb_max"])
