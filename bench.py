@@ -60,7 +60,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -69,6 +69,15 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        """samples taken from now on are the ones reported (the load window)"""
+        self.first = len(self.rows)
 
     def stop(self):
         if self.proc:
@@ -79,7 +88,7 @@ class ClockSampler:
                 self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[getattr(self, "first", 0):]:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -190,8 +199,7 @@ def main():
         dist.broadcast_object_list(meta, src=0)
         blob = torch.empty(meta[0], dtype=torch.uint8, device="cuda")
         if rank == 0:
-            ptr, nbytes = ctx.scene_blob()
-            assert int(torch.cuda.cudart().cudaMemcpy(blob.data_ptr(), ptr, nbytes, 3)) == 0
+            ctx.copy_scene_blob(blob, blob.numel())
         pt = torch.from_numpy(params).cuda()
         torch.cuda.synchronize()
         dist.barrier()
@@ -230,14 +238,17 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             step()
     barrier()
+    sampler.wait_first()
+    # keep the GPU under the same load until the sampler has started delivering, then open the window
+    sampler.mark()
 
     # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps ------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ctx.reset_counters()
     step_ms = []
     barrier()
@@ -254,7 +265,6 @@ def main():
         step_ms.append(e0.elapsed_time(e1))
     barrier()
     launches = ctx.counters()["kernel_launches"] + (args.steps if world > 1 else 0)  # + our band-pack copy per step
-    clocks = sampler.stop()
     total_ms = float(np.sum(step_ms))
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -304,6 +314,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": rays_total * args.steps / float(t.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 128 * world,
                "d2h_bytes_per_step": int(host_frame.numel() * 4), "call": "rt_set_params + rt_primary_device(bands) + NCCL all_gather + frame D2H on rank 0"}
+
+    # clocks: the sampling window covers the K timed steps and the e2e loop; if the timed steps were shorter than
+    # two sampling periods, extend the window with more (untimed) steps of the same load
+    with torch.cuda.stream(stream):
+        t_end = time.time() + 0.4
+        while time.time() < t_end:
+            step()
+            stream.synchronize()
+    clocks = sampler.stop()
 
     # ---- rank 0: CPU baseline + roofline, then the JSON line ---------------------------------------
     if rank == 0:

@@ -91,6 +91,8 @@ int rt_upload_scene(rt_context* ctx, const float* verts, int V, const int32_t* i
 /* The packed device scene is ONE contiguous, position-independent device allocation so that it can
  * be broadcast to other GPUs as a single buffer (NCCL) and adopted there without a host round trip. */
 int rt_scene_blob(rt_context* ctx, void** out_device_ptr, size_t* out_bytes);
+/* Device-to-device copy of the blob into caller-owned device memory (e.g. the NCCL broadcast buffer). */
+int rt_copy_scene_blob(rt_context* ctx, void* dst_device_ptr, size_t bytes);
 /* Adopt a blob that already sits in this device's memory (borrowed: the caller keeps it alive). */
 int rt_adopt_scene_blob(rt_context* ctx, void* device_ptr, size_t bytes);
 
@@ -142,6 +144,9 @@ int rt_get_counters(rt_context* ctx, uint64_t out[RT_CNT_COUNT]);
 int rt_reset_counters(rt_context* ctx);
 /* Traversal variant selector for experiments (see DESIGN.md "Kernels"); 0 = default. */
 int rt_set_option(rt_context* ctx, const char* name, int value);
+/* GPU self test of the box test's hoisted exact division against the compiler's IEEE division on
+ * `samples` random operand pairs; *out_mismatches must come back 0. */
+int rt_selftest(rt_context* ctx, int64_t samples, uint32_t seed, uint64_t* out_mismatches);
 /* Scene statistics: [0] node pairs, [1] packed triangles, [2] blob bytes, [3] max tree depth */
 int rt_scene_info(rt_context* ctx, int64_t out[4]);
 

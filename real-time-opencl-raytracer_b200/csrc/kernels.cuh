@@ -336,4 +336,34 @@ __global__ void diffuse_rays_kernel(SceneView s, long long n, const float4* rays
     }
 }
 
+// ---- self test: div_hoisted(x, d, div_prepare(d)) must equal x / d bit for bit over the admitted window ---
+// d: any sign, exponent in [-20, 20]; x: 0 or any sign, exponent in [-43, 21]; mantissas random or edge patterns.
+__global__ void selftest_division_kernel(unsigned int seed, int iters, unsigned long long* mismatches) {
+    const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int state = lowbias32(tid ^ (seed * 0x9e3779b9u));
+    const unsigned int edge[8] = {0u, 0x7FFFFFu, 0x400000u, 1u, 0x7FFFFEu, 0x555555u, 0x2AAAAAu, 0x7FF000u};
+    unsigned long long bad = 0;
+    for (int i = 0; i < iters; i++) {
+        state = lowbias32(state + 0x6a09e667u);
+        const unsigned int a = state;
+        state = lowbias32(state + 0xbb67ae85u);
+        const unsigned int b = state;
+        state = lowbias32(state + 0x3c6ef372u);
+        const unsigned int c = state;
+        unsigned int md = a & 0x7FFFFFu, mx = b & 0x7FFFFFu;
+        if ((c & 7u) == 0u) md = edge[(c >> 3) & 7u];
+        if ((c & 0x38u) == 0u) mx = edge[(c >> 6) & 7u];
+        const unsigned int ed = 127u - 20u + ((c >> 9) % 41u);   // exponent -20..20
+        const unsigned int ex = 127u - 43u + ((c >> 16) % 65u);  // exponent -43..21
+        const float d = __uint_as_float(((a >> 31) << 31) | (ed << 23) | md);
+        float x = __uint_as_float(((b >> 31) << 31) | (ex << 23) | mx);
+        if ((c >> 24) == 0u) x = 0.0f;
+        if (fabsf(d) > 1048576.0f) continue;  // exponent 20 with a non-zero mantissa is outside the window
+        const float want = x / d;
+        const float got = div_hoisted(x, d, div_prepare(d));
+        if (__float_as_uint(want) != __float_as_uint(got) && !(want == 0.0f && got == 0.0f)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace rtb

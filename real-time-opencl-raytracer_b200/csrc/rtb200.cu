@@ -51,6 +51,7 @@ struct rt_context {
     int opt_smem_top = 0;     // number of top pairs staged in shared memory (0 = off)
     int opt_blocks_per_sm = 0;  // 0 = occupancy-derived
     int opt_top_pairs = 2047;   // BFS-ordered prefix chosen at pack time
+    int opt_exact_div = 0;      // 1 = always use the compiler's full division in the box test
     uint64_t counters[RT_CNT_COUNT] = {0};
     std::string err;
 };
@@ -167,6 +168,7 @@ static int bind_blob(rt_context* ctx, const BlobHeader& h, uint8_t* d_blob, size
     v.root_ref = h.root_ref;
     v.num_pairs = h.num_pairs;
     v.top_pairs = h.top_pairs;
+    v.coords_in_window = ctx->opt_exact_div ? 0 : h.coords_in_window;
     ctx->have_scene = true;
     return RT_OK;
 }
@@ -205,6 +207,16 @@ extern "C" int rt_scene_blob(rt_context* ctx, void** out_device_ptr, size_t* out
     return RT_OK;
 }
 
+extern "C" int rt_copy_scene_blob(rt_context* ctx, void* dst_device_ptr, size_t bytes) {
+    if (!ctx || !dst_device_ptr) return RT_E_INVALID;
+    if (!ctx->have_scene) return set_err(ctx, RT_E_NO_SCENE, "rt_copy_scene_blob: no scene uploaded");
+    if (bytes != ctx->blob_bytes) return set_err(ctx, RT_E_INVALID, "rt_copy_scene_blob: %zu bytes given, blob has %zu", bytes, ctx->blob_bytes);
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(dst_device_ptr, ctx->d_blob, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
 extern "C" int rt_adopt_scene_blob(rt_context* ctx, void* device_ptr, size_t bytes) {
     if (!ctx || !device_ptr || bytes < sizeof(BlobHeader)) return RT_E_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
@@ -225,7 +237,10 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     if (!ctx || !name) return RT_E_INVALID;
     if (!strcmp(name, "smem_top")) ctx->opt_smem_top = value < 0 ? 0 : value;
     else if (!strcmp(name, "blocks_per_sm")) ctx->opt_blocks_per_sm = value < 0 ? 0 : value;
-    else if (!strcmp(name, "top_pairs")) ctx->opt_top_pairs = value < 0 ? 0 : value;  // takes effect at the next upload
+    else if (!strcmp(name, "exact_div")) {
+        ctx->opt_exact_div = value ? 1 : 0;
+        if (ctx->have_scene) ctx->view.coords_in_window = ctx->opt_exact_div ? 0 : ctx->hdr.coords_in_window;
+    } else if (!strcmp(name, "top_pairs")) ctx->opt_top_pairs = value < 0 ? 0 : value;  // takes effect at the next upload
     else return set_err(ctx, RT_E_INVALID, "rt_set_option: unknown option '%s'", name);
     return RT_OK;
 }
@@ -496,5 +511,23 @@ extern "C" int rt_render_frame(rt_context* ctx, int w, int h, uint32_t* out_host
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->counters[RT_CNT_H2D_BYTES] += sizeof(ParamsBlock);
     ctx->counters[RT_CNT_D2H_BYTES] += bytes;
+    return RT_OK;
+}
+
+// GPU self test of the hoisted division (device_math.cuh): `samples` random operand pairs inside the
+// admitted window, bitwise comparison against the compiler's IEEE division.
+extern "C" int rt_selftest(rt_context* ctx, int64_t samples, uint32_t seed, uint64_t* out_mismatches) {
+    if (!ctx || !out_mismatches || samples < 1) return RT_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemsetAsync(ctx->d_counter + 8, 0, sizeof(unsigned long long), ctx->stream));
+    const int threads = 256, iters = 4096;
+    long long blocks = (samples + (long long)threads * iters - 1) / ((long long)threads * iters);
+    if (blocks < 1) blocks = 1;
+    selftest_division_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(seed, iters, ctx->d_counter + 8);
+    CK(ctx, cudaGetLastError());
+    unsigned long long bad = 0;
+    CK(ctx, cudaMemcpyAsync(&bad, ctx->d_counter + 8, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_mismatches = bad;
     return RT_OK;
 }

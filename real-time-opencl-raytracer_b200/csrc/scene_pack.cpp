@@ -148,6 +148,13 @@ int pack_scene(const SceneInputs& in, int top_pairs, uint8_t** out_blob, uint64_
     h.root_ref = child_ref(0);
 
     float* pairs = (float*)(blob + h.off_pairs);
+    bool in_window = true;
+    auto check = [&in_window](const float* c) {
+        for (int k = 0; k < 3; k++) {
+            const float a = c[k] < 0 ? -c[k] : c[k];
+            if (!(c[k] == 0.0f || (a >= 9.5367431640625e-07f && a <= 1048576.0f))) in_window = false;
+        }
+    };
     for (int p = 0; p < P; p++) {
         const RefNode& n = nodes[order[p]];
         const RefNode &c0 = nodes[n.left], &c1 = nodes[n.right];
@@ -156,7 +163,9 @@ int pack_scene(const SceneInputs& in, int top_pairs, uint8_t** out_blob, uint64_
         q[4] = c0.mx[0]; q[5] = c0.mx[1]; q[6] = c0.mx[2]; q[7] = 0.0f;
         q[8] = c1.mn[0]; q[9] = c1.mn[1]; q[10] = c1.mn[2]; q[11] = as_float(child_ref(n.right));
         q[12] = c1.mx[0]; q[13] = c1.mx[1]; q[14] = c1.mx[2]; q[15] = 0.0f;
+        check(c0.mn); check(c0.mx); check(c1.mn); check(c1.mx);
     }
+    h.coords_in_window = in_window ? 1 : 0;
 
     // ---- triangles in tri_indices order; `last` set from the leaves
     float* tris = (float*)(blob + h.off_tris);

@@ -34,6 +34,7 @@ struct SceneView {
     int root_ref;
     int num_pairs;
     int top_pairs;
+    int coords_in_window;  // every box coordinate is 0 or within the hoisted division's window (set at pack time)
 };
 
 struct TraceResult {
@@ -45,6 +46,7 @@ struct TraceResult {
 template <bool ANY_HIT, bool SMEM_TOP>
 __device__ __forceinline__ TraceResult traverse(const SceneView& s, const float4* __restrict__ smem_pairs, int smem_count,
                                                 const Ray& ray, float tHit) {
+    const RayX rx = ray_prepare(ray, s.coords_in_window != 0);
     int stack[RTB_STACK];
     int sp = 0;
     int cur = s.root_ref;
@@ -65,8 +67,13 @@ __device__ __forceinline__ TraceResult traverse(const SceneView& s, const float4
                 q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
             }
             float t0n, t0f, t1n, t1f;
-            ray_box(ray, q0, q1, t0n, t0f);
-            ray_box(ray, q2, q3, t1n, t1f);
+            if (rx.fast) {
+                ray_box_hoisted(rx, q0, q1, t0n, t0f);
+                ray_box_hoisted(rx, q2, q3, t1n, t1f);
+            } else {
+                ray_box(ray, q0, q1, t0n, t0f);
+                ray_box(ray, q2, q3, t1n, t1f);
+            }
             const bool hit0 = (t0n <= t0f) && (t0f >= RTB_TMIN) && (t0n <= tHit);
             const bool hit1 = (t1n <= t1f) && (t1f >= RTB_TMIN) && (t1n <= tHit);
             int c0 = __float_as_int(q0.w), c1 = __float_as_int(q2.w);

@@ -19,9 +19,9 @@ HIT_DTYPE = np.dtype([("idx", np.int32), ("t", np.float32), ("u", np.float32), (
 
 ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_version", "rt_set_stream", "rt_synchronize", "rt_upload_scene",
-    "rt_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_primary", "rt_trace_device",
+    "rt_scene_blob", "rt_copy_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_primary", "rt_trace_device",
     "rt_primary_device", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
-    "rt_reset_counters", "rt_set_option", "rt_scene_info",
+    "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest",
 ]
 
 
@@ -46,6 +46,7 @@ def lib():
         L.rt_upload_scene.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp]
         L.rt_scene_blob.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
         L.rt_adopt_scene_blob.argtypes = [vp, vp, C.c_size_t]
+        L.rt_copy_scene_blob.argtypes = [vp, vp, C.c_size_t]
         L.rt_set_params.argtypes = [vp, vp]
         L.rt_render_frame.argtypes = [vp, i32, i32, vp]
         L.rt_trace.argtypes = [vp, i32, i64, vp, vp]
@@ -59,6 +60,7 @@ def lib():
         L.rt_reset_counters.argtypes = [vp]
         L.rt_set_option.argtypes = [vp, C.c_char_p, i32]
         L.rt_scene_info.argtypes = [vp, vp]
+        L.rt_selftest.argtypes = [vp, i64, C.c_uint32, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -123,6 +125,11 @@ class Context:
     def reset_counters(self):
         self._ck(lib().rt_reset_counters(self._h))
 
+    def selftest(self, samples, seed=1):
+        bad = C.c_uint64(0)
+        self._ck(lib().rt_selftest(self._h, samples, seed, C.byref(bad)))
+        return int(bad.value)
+
     def scene_info(self):
         out = np.zeros(4, dtype=np.int64)
         self._ck(lib().rt_scene_info(self._h, out.ctypes.data))
@@ -150,6 +157,9 @@ class Context:
         p, n = C.c_void_p(), C.c_size_t()
         self._ck(lib().rt_scene_blob(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def copy_scene_blob(self, dst, nbytes):
+        self._ck(lib().rt_copy_scene_blob(self._h, _ptr(dst), nbytes))
 
     def adopt_scene_blob(self, device_ptr, nbytes):
         self._ck(lib().rt_adopt_scene_blob(self._h, device_ptr, nbytes))

@@ -83,6 +83,24 @@ def test_render_frame_vs_golden(ctx, name):
     assert np.all(img >> 24 == 0)
 
 
+def test_hoisted_division_is_the_ieee_quotient(ctx):
+    """the box test's per-ray-hoisted division (FMUL + 2 FFMA) == `/` bit for bit on 2 G random operand pairs"""
+    for seed in (1, 2):
+        assert ctx.selftest(1 << 30, seed) == 0
+
+
+@pytest.mark.parametrize("exact_div", [0, 1])
+def test_exact_div_option_gives_identical_results(ctx, exact_div):
+    g = load_scene("mix")
+    _upload(ctx, g)
+    ctx.set_option("exact_div", exact_div)
+    try:
+        assert_hits_identical(ctx.trace(rtb200.CLOSEST, g["random_rays"]), g["random_hits_closest"].view(HIT).reshape(-1), "closest")
+        assert_hits_identical(ctx.trace(rtb200.ANY, g["random_rays"]), g["random_hits_any"].view(HIT).reshape(-1), "any")
+    finally:
+        ctx.set_option("exact_div", 0)
+
+
 @pytest.mark.parametrize("smem_top", [0, 63, 500])
 def test_smem_top_variant_is_identical(ctx, smem_top):
     g = load_scene("mix")
@@ -235,17 +253,15 @@ def test_scene_blob_adopt_roundtrip(ctx):
     g = load_scene("mix")
     _upload(ctx, g)
     ptr, nbytes = ctx.scene_blob()
-    src = torch.empty(0, dtype=torch.uint8, device="cuda")
-    import ctypes as C
-
+    assert ptr and nbytes == ctx.scene_info()["blob_bytes"]
     clone = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-    cudart = torch.cuda.cudart()
-    assert int(cudart.cudaMemcpy(clone.data_ptr(), ptr, nbytes, 3)) == 0  # cudaMemcpyDeviceToDevice
+    ctx.copy_scene_blob(clone, nbytes)
+    moved = clone.clone()  # a second copy at a different address: the blob is position independent
+    del clone
     c2 = rtb200.Context(0)
-    c2.adopt_scene_blob(clone.data_ptr(), nbytes)
+    c2.adopt_scene_blob(moved.data_ptr(), nbytes)
     assert_hits_identical(c2.trace(rtb200.ANY, g["random_rays"]), g["random_hits_any"].view(HIT).reshape(-1), "adopted blob")
     c2.close()
-    del src, C
 
 
 def test_full_size_properties(ctx):
