@@ -225,6 +225,24 @@ static void trace_impl(const orc_scene* s, int mode, int64_t n, const float* ray
     if (counters) { counters[0] = ci; counters[1] = cl; counters[2] = ct; counters[3] = cm; }
 }
 
+/* per-ray visit counts (inner, leaf, tris) for workload analysis: stats[3*i + {0,1,2}] */
+void orc_trace_stats(const orc_scene* s, int mode, int64_t n, const float* rays, void* hits_v, uint32_t* stats) {
+    Hit* hits = (Hit*)hits_v;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; i++) {
+        const float* r8 = rays + i * 8;
+        Ray r;
+        r.ori = mk3(r8[0], r8[1], r8[2]);
+        r.dir = mk3(r8[4], r8[5], r8[6]);
+        r.inv_dir = mk3(0, 0, 0);
+        float tHit = r8[3], u = 0.f, v = 0.f;
+        Counters c = {0, 0, 0, 0};
+        int idx = traverse_bvh(s, &r, &tHit, mode == 0, &u, &v, &c);
+        hits[i].idx = idx; hits[i].t = tHit; hits[i].u = idx >= 0 ? u : 0.f; hits[i].v = idx >= 0 ? v : 0.f;
+        stats[3 * i] = (uint32_t)c.inner; stats[3 * i + 1] = (uint32_t)c.leaf; stats[3 * i + 2] = (uint32_t)c.tris;
+    }
+}
+
 void orc_trace(const orc_scene* s, int mode, int64_t n, const float* rays, void* hits, uint64_t* counters) {
     trace_impl(s, mode, n, rays, hits, counters, 0);
 }

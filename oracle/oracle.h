@@ -50,6 +50,9 @@ typedef struct {
  *                                   [3] max stack depth seen. */
 void orc_trace(const orc_scene* s, int mode, int64_t n, const float* rays, void* hits, uint64_t* counters);
 
+/* same as orc_trace, additionally stats[3*i+{0,1,2}] = inner visits, leaf visits, triangle tests of ray i */
+void orc_trace_stats(const orc_scene* s, int mode, int64_t n, const float* rays, void* hits, uint32_t* stats);
+
 /* brute-force loop of volumeRender.cl:690-712 (the author's "works !!!" body), same outputs */
 void orc_trace_bruteforce(const orc_scene* s, int mode, int64_t n, const float* rays, void* hits);
 

@@ -1,0 +1,202 @@
+// kernels_lanes.cuh -- "persistent lanes" scheduler around the same per-ray traversal semantics.
+//
+// trace_kernel (kernels.cuh) gives every warp a batch of 32 rays and runs traverse() to completion:
+// lanes whose ray ends early idle until the slowest ray of the batch is done, and lanes drift apart
+// between the inner-node loop and the leaf loop (ncu: 16.3 of 32 threads active per instruction).
+// Here a lane is the unit of scheduling:
+//   * REFILL   lanes without a ray take the next work items from a warp-local chunk of the global
+//              queue (one atomicAdd by lane 0 per chunk, ballot + popc give each empty lane its item)
+//              as soon as `refill_threshold` lanes are empty
+//   * INNER    all lanes that stand on an inner node do node-pair visits in lock step (warp-uniform
+//              loop on a ballot); a lane drops out when it reaches a leaf or finishes its ray
+//   * LEAF     all lanes that stand on a leaf test that leaf's triangles together
+// Per ray, the sequence of box tests, pushes, pops and triangle tests is exactly the one of traverse():
+// results are bit-identical; only WHEN a lane executes its next step changes.
+#pragma once
+#include "kernels.cuh"
+
+namespace rtb {
+
+static constexpr int kLaneChunk = 128;  // work items a warp takes from the global queue per atomicAdd
+
+template <int SRC, bool ANY_HIT>
+__global__ void __launch_bounds__(kBlockThreads) trace_lanes_kernel(const TraceArgs a, int refill_threshold, int inner_exit_threshold) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned long long total = (SRC == SRC_PRIMARY) ? (unsigned long long)a.num_batches * 32ull : (unsigned long long)a.n;
+
+    // warp-local slice of the work queue
+    unsigned long long q_next = 0, q_end = 0;
+    bool queue_open = true;
+
+    // lane state
+    bool has_ray = false;
+    Ray ray;
+    RayX rx;
+    float tHit = RTB_T_INIT;
+    TraceResult res;
+    long long out_index = 0;
+    int cur = 0, sp = 0;
+    int stack[RTB_STACK];
+    ray.ori = ray.dir = mk3(0.f, 0.f, 1.f);
+    rx = ray_prepare(ray, false);
+    res.idx = -1; res.t = 0.f; res.u = 0.f; res.v = 0.f;
+
+    for (;;) {
+        // ---- REFILL ----------------------------------------------------------------------------
+        const unsigned empty = __ballot_sync(FULL, !has_ray);
+        const int n_empty = __popc(empty);
+        if (queue_open && n_empty >= refill_threshold) {
+            const unsigned long long avail = q_end - q_next;
+            unsigned long long fresh = 0;
+            if ((unsigned long long)n_empty > avail) {  // warp-uniform
+                if (lane == 0) fresh = atomicAdd(a.work_counter, (unsigned long long)kLaneChunk);
+                fresh = __shfl_sync(FULL, fresh, 0);
+            }
+            const unsigned rank = __popc(empty & lt_mask);
+            unsigned long long item = total;  // "nothing"
+            if (!has_ray) {
+                if (rank < avail) item = q_next + rank;
+                else if ((unsigned long long)n_empty > avail) item = fresh + (rank - avail);
+            }
+            if ((unsigned long long)n_empty > avail) {
+                q_next = fresh + ((unsigned long long)n_empty - avail);
+                q_end = fresh + kLaneChunk;
+                if (fresh >= total) queue_open = false;
+            } else {
+                q_next += n_empty;
+            }
+            if (item < total) {
+                bool active = false;
+                tHit = RTB_T_INIT;
+                if (SRC == SRC_BUFFER) {
+                    const float4 o = __ldg(a.rays_in + 2 * item), d = __ldg(a.rays_in + 2 * item + 1);
+                    ray.ori = ld3(o);
+                    ray.dir = ld3(d);
+                    tHit = o.w;
+                    out_index = (long long)item;
+                    active = true;
+                } else if (SRC == SRC_PRIMARY) {
+                    int x, y;
+                    tile_pixel(a, (long long)(item >> 5), (int)(item & 31), x, y);
+                    if (x < a.w && y < a.h) {
+                        out_index = (long long)y * a.w + x;
+                        active = primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray);
+                        if (a.rays_out) store_ray(a.rays_out, out_index, ray);
+                        if (!active) a.hits_out[out_index] = make_float4(__int_as_float(-1), RTB_T_INIT, 0.0f, 0.0f);
+                    }
+                } else {  // SRC_SHADOW
+                    out_index = (long long)item;
+                    const float4 hin = __ldg(a.hits_in + item);
+                    if (__float_as_int(hin.x) >= 0) {
+                        const float4 o = __ldg(a.rays_in + 2 * item), d = __ldg(a.rays_in + 2 * item + 1);
+                        Ray pr;
+                        pr.ori = ld3(o);
+                        pr.dir = ld3(d);
+                        f3 hp;
+                        ray = shadow_ray(ld3(a.params.light_pos), pr, hin.y, hp);
+                        active = true;
+                        if (a.rays_out) store_ray(a.rays_out, out_index, ray);
+                    } else {
+                        a.hits_out[item] = make_float4(__int_as_float(-1), RTB_T_INIT, 0.0f, 0.0f);
+                        if (a.rays_out) {
+                            a.rays_out[2 * item] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            a.rays_out[2 * item + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                }
+                if (active) {
+                    rx = ray_prepare(ray, a.scene.coords_in_window != 0);
+                    cur = a.scene.root_ref;
+                    sp = 0;
+                    res.idx = -1;
+                    res.u = res.v = 0.0f;
+                    has_ray = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, has_ray)) {
+            if (!queue_open) break;
+            continue;
+        }
+
+        // ---- INNER: node-pair visits in lock step -----------------------------------------------
+        for (;;) {
+            const bool inner = has_ray && cur >= 0;
+            const unsigned m = __ballot_sync(FULL, inner);
+            if (m == 0) break;
+            if (__popc(m) < inner_exit_threshold && __ballot_sync(FULL, has_ray && cur < 0) != 0) break;
+            if (inner) {
+                const float4* p = a.scene.pairs + 4 * (size_t)cur;
+                const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+                float t0n, t0f, t1n, t1f;
+                if (rx.fast) {
+                    ray_box_hoisted(rx, q0, q1, t0n, t0f);
+                    ray_box_hoisted(rx, q2, q3, t1n, t1f);
+                } else {
+                    ray_box(ray, q0, q1, t0n, t0f);
+                    ray_box(ray, q2, q3, t1n, t1f);
+                }
+                const bool hit0 = (t0n <= t0f) && (t0f >= RTB_TMIN) && (t0n <= tHit);
+                const bool hit1 = (t1n <= t1f) && (t1f >= RTB_TMIN) && (t1n <= tHit);
+                int c0 = __float_as_int(q0.w), c1 = __float_as_int(q2.w);
+                if (hit0 && hit1) {
+                    if (t0n > t1n) { const int t = c0; c0 = c1; c1 = t; }
+                    if (sp >= RTB_STACK) {  // reference: stack overflow returns -1 and drops the hit (vR.cl:914)
+                        a.hits_out[out_index] = make_float4(__int_as_float(-1), tHit, 0.0f, 0.0f);
+                        has_ray = false;
+                    } else {
+                        stack[sp++] = c1;
+                        cur = c0;
+                    }
+                } else if (hit0) {
+                    cur = c0;
+                } else if (hit1) {
+                    cur = c1;
+                } else if (sp == 0) {
+                    a.hits_out[out_index] = make_float4(__int_as_float(res.idx), tHit, res.u, res.v);
+                    has_ray = false;
+                } else {
+                    cur = stack[--sp];
+                }
+            }
+        }
+
+        // ---- LEAF: the triangles of the leaf each lane stands on ------------------------------------
+        if (has_ray && cur < 0) {
+            bool done = false;
+            if (cur == kRefPoison) {  // vR.cl:841,855-856
+                res.idx = -1; res.u = res.v = 0.0f;
+                done = true;
+            } else {
+                const float4* tp = a.scene.tris + 3 * (size_t)(~cur);
+                for (;;) {
+                    const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+                    float u, v;
+                    const float t = ray_triangle(ray, ld3(ta), ld3(tb), ld3(tc), u, v);
+                    if (t < tHit && t > RTB_TMIN) {
+                        tHit = t;
+                        res.idx = __float_as_int(ta.w);
+                        res.u = u;
+                        res.v = v;
+                        if (ANY_HIT) { done = true; break; }
+                    }
+                    if (__float_as_int(tb.w) != 0) break;
+                    tp += 3;
+                }
+                if (!done) {
+                    if (sp == 0) done = true;
+                    else cur = stack[--sp];
+                }
+            }
+            if (done) {
+                a.hits_out[out_index] = make_float4(__int_as_float(res.idx), tHit, res.u, res.v);
+                has_ray = false;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace rtb

@@ -13,6 +13,7 @@
 #include <string>
 
 #include "kernels.cuh"
+#include "kernels_lanes.cuh"
 #include "scene_blob.h"
 
 using namespace rtb;
@@ -51,6 +52,10 @@ struct rt_context {
     int opt_smem_top = 0;     // number of top pairs staged in shared memory (0 = off)
     int opt_blocks_per_sm = 0;  // 0 = occupancy-derived
     int opt_top_pairs = 2047;   // BFS-ordered prefix chosen at pack time
+    int opt_scheduler = -1;     // 0 = one 32-ray batch per warp (trace_kernel), 1 = persistent lanes (trace_lanes_kernel),
+                                // -1 = auto: batch for in-kernel camera/shadow rays (coherent), lanes for ray buffers
+    int opt_refill = 16;         // persistent lanes: refill when this many lanes are empty
+    int opt_inner_exit = 8;     // persistent lanes: leave the inner phase when fewer lanes than this still descend
     int opt_exact_div = 0;      // 1 = always use the compiler's full division in the box test
     uint64_t counters[RT_CNT_COUNT] = {0};
     std::string err;
@@ -237,6 +242,9 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     if (!ctx || !name) return RT_E_INVALID;
     if (!strcmp(name, "smem_top")) ctx->opt_smem_top = value < 0 ? 0 : value;
     else if (!strcmp(name, "blocks_per_sm")) ctx->opt_blocks_per_sm = value < 0 ? 0 : value;
+    else if (!strcmp(name, "scheduler")) ctx->opt_scheduler = value < 0 ? -1 : (value ? 1 : 0);
+    else if (!strcmp(name, "refill")) ctx->opt_refill = value < 1 ? 1 : (value > 32 ? 32 : value);
+    else if (!strcmp(name, "inner_exit")) ctx->opt_inner_exit = value < 0 ? 0 : (value > 32 ? 32 : value);
     else if (!strcmp(name, "exact_div")) {
         ctx->opt_exact_div = value ? 1 : 0;
         if (ctx->have_scene) ctx->view.coords_in_window = ctx->opt_exact_div ? 0 : ctx->hdr.coords_in_window;
@@ -289,6 +297,25 @@ static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, int smem_c
     return RT_OK;
 }
 
+template <typename K>
+static int launch_lanes(rt_context* ctx, K kernel, TraceArgs& a, long long total_items) {
+    int per_sm = ctx->opt_blocks_per_sm;
+    if (per_sm <= 0) {
+        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, 0));
+        if (per_sm < 1) per_sm = 1;
+    }
+    long long blocks = (long long)per_sm * ctx->num_sms;
+    const long long needed = (total_items + kBlockThreads - 1) / kBlockThreads;
+    if (blocks > needed) blocks = needed;
+    if (blocks < 1) return RT_OK;
+    a.work_counter = ctx->d_counter;
+    CK(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
+    kernel<<<(unsigned)blocks, kBlockThreads, 0, ctx->stream>>>(a, ctx->opt_refill, ctx->opt_inner_exit);
+    CK(ctx, cudaGetLastError());
+    ctx->counters[RT_CNT_KERNEL_LAUNCHES]++;
+    return RT_OK;
+}
+
 static int smem_top_count(const rt_context* ctx) {
     int c = ctx->opt_smem_top;
     if (c > ctx->hdr.top_pairs) c = ctx->hdr.top_pairs;
@@ -331,7 +358,10 @@ static int do_trace_device(rt_context* ctx, int mode, long long n, const rt_ray*
     a.hits_out = (float4*)d_hits;
     const int st = smem_top_count(ctx);
     int rc;
-    if (mode == RT_CLOSEST)
+    if (ctx->opt_scheduler != 0 && !st)
+        rc = mode == RT_CLOSEST ? launch_lanes(ctx, trace_lanes_kernel<SRC_BUFFER, false>, a, n)
+                                : launch_lanes(ctx, trace_lanes_kernel<SRC_BUFFER, true>, a, n);
+    else if (mode == RT_CLOSEST)
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, true>, a, st)
                 : launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false>, a, 0);
     else
@@ -393,8 +423,11 @@ extern "C" int rt_primary_device(rt_context* ctx, int w, int h, int part, int n_
     a.hits_out = (float4*)d_hits;
     a.rays_out = (float4*)d_rays_out;
     const int st = smem_top_count(ctx);
-    rc = st ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, true>, a, st)
-            : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0);
+    if (ctx->opt_scheduler == 1 && !st)
+        rc = launch_lanes(ctx, trace_lanes_kernel<SRC_PRIMARY, false>, a, a.num_batches * 32);
+    else
+        rc = st ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, true>, a, st)
+                : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0);
     if (rc == RT_OK) ctx->counters[RT_CNT_RAYS_TRACED] += (uint64_t)a.num_batches * 32;
     return rc;
 }
@@ -445,8 +478,11 @@ extern "C" int rt_shadow_device(rt_context* ctx, int64_t n, const rt_ray* d_rays
     a.hits_out = (float4*)d_shadow_hits;
     a.rays_out = (float4*)d_shadow_rays_out;
     const int st = smem_top_count(ctx);
-    rc = st ? launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, true>, a, st)
-            : launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, false>, a, 0);
+    if (ctx->opt_scheduler == 1 && !st)
+        rc = launch_lanes(ctx, trace_lanes_kernel<SRC_SHADOW, true>, a, n);
+    else
+        rc = st ? launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, true>, a, st)
+                : launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, false>, a, 0);
     if (rc == RT_OK) ctx->counters[RT_CNT_RAYS_TRACED] += (uint64_t)n;
     return rc;
 }
