@@ -195,42 +195,40 @@ def main():
     else:
         params = np.zeros(32, dtype=np.float32)
     if world > 1:
-        meta = [ctx.scene_blob()[1] if rank == 0 else 0]
-        dist.broadcast_object_list(meta, src=0)
-        blob = torch.empty(meta[0], dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            ctx.copy_scene_blob(blob, blob.numel())
+        from rtb200 import tiling
+
         pt = torch.from_numpy(params).cuda()
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        dist.broadcast(blob, src=0)  # NCCL over NVLink: the packed BVH + triangles
+        blob = tiling.broadcast_scene(dist, ctx, rank, "cuda")  # NCCL over NVLink: the packed BVH + triangles, one buffer
         dist.broadcast(pt, src=0)
         e1.record()
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
         params = pt.cpu().numpy()
-        ctx.adopt_scene_blob(blob.data_ptr(), blob.numel())
     ctx.set_params(params)
 
     # ---- buffers ---------------------------------------------------------------------------------
     d_hits = torch.zeros((n_pix, 4), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    owned_rows = [y for y in range(h) if (y // BAND_ROWS) % world == rank]
     if world > 1:
         # per-rank band buffer (4 B/pixel hit index) -> all_gather -> frame
-        rows_per_rank = max(len([y for y in range(h) if (y // BAND_ROWS) % world == r]) for r in range(world))
-        band_idx = torch.tensor(owned_rows + [owned_rows[-1]] * (rows_per_rank - len(owned_rows)), device="cuda")
+        owned_rows = list(tiling.owned_rows(rank, world, h, BAND_ROWS))
+        rows_per_rank = tiling.rows_per_rank(world, h, BAND_ROWS)
+        band_idx = tiling.band_index(rank, world, h, BAND_ROWS, device="cuda")
         d_band = torch.empty((rows_per_rank, w), dtype=torch.int32, device="cuda")
         d_gather = torch.empty((world, rows_per_rank, w), dtype=torch.int32, device="cuda")
+    else:
+        owned_rows = list(range(h))
 
     def step():
         ctx.primary_device(w, h, d_hits, None, part=rank, n_parts=world, band_rows=BAND_ROWS)
         if world > 1:
             with torch.cuda.stream(stream):
                 torch.index_select(d_hits.view(torch.int32).view(h, w, 4)[:, :, 0], 0, band_idx, out=d_band)
-                dist.all_gather_into_tensor(d_gather, d_band)
+                tiling.gather_bands(dist, d_band, out=d_gather)
 
     def barrier():
         torch.cuda.synchronize()

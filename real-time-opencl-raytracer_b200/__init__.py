@@ -6,6 +6,6 @@ intersection) of itmanager85/real-time-opencl-raytracer behind a C ABI (include/
   device.py / hostlib.py   thin ctypes views of the two libraries for tests and bench.py
 
 The directory name contains hyphens, so import it through the `rtb200` shim at the repo root."""
-from . import device, hostlib  # noqa: F401
+from . import device, hostlib, tiling  # noqa: F401
 from .device import ANY, CLOSEST, HIT_DTYPE, RAY_DTYPE, T_INIT, Context, RtError  # noqa: F401
 from .hostlib import FlatBVH, Mesh, camera_params  # noqa: F401

@@ -1,0 +1,67 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): screen-space partition, the one-off
+scene broadcast, and the per-frame framebuffer gather -- the only collectives of the path.
+
+Partition = interleaved bands of `band_rows` rows (a multiple of the kernel's 4-row warp tile): band b
+belongs to rank b % world, which balances sky against terrain. Every rank holds the whole packed scene.
+The reference has no multi-device code; this is new.
+
+Everything here is backend agnostic: NCCL over NVLink on GPUs, gloo in the CPU tests."""
+import numpy as np
+import torch
+
+
+def owned_rows(rank, world, h, band_rows):
+    """Row indices (ascending) that `rank` renders."""
+    if band_rows < 4 or band_rows % 4:
+        raise ValueError("band_rows must be a positive multiple of 4")
+    ys = np.arange(h)
+    return ys[(ys // band_rows) % world == rank]
+
+
+def rows_per_rank(world, h, band_rows):
+    """Rows of the largest share: every rank's band buffer is padded to this so the gather is uniform."""
+    return max(len(owned_rows(r, world, h, band_rows)) for r in range(world))
+
+
+def band_index(rank, world, h, band_rows, device=None):
+    """Index tensor that picks this rank's rows out of a full (h, w) frame, padded by repeating the last row."""
+    rows = owned_rows(rank, world, h, band_rows)
+    n = rows_per_rank(world, h, band_rows)
+    if len(rows) == 0:
+        rows = np.zeros(1, dtype=np.int64)
+    padded = np.concatenate([rows, np.full(n - len(rows), rows[-1])])
+    return torch.as_tensor(padded, dtype=torch.int64, device=device)
+
+
+def gather_bands(dist, band, out=None):
+    """all_gather of the per-rank band buffers (rows_per_rank, w) -> (world, rows_per_rank, w)."""
+    world = dist.get_world_size()
+    if out is None:
+        out = torch.empty((world,) + tuple(band.shape), dtype=band.dtype, device=band.device)
+    # a list of views into one contiguous buffer: one collective on NCCL, and accepted by gloo as well
+    dist.all_gather(list(out.unbind(0)), band.contiguous())
+    return out
+
+
+def assemble_frame(gathered, h, band_rows):
+    """(world, rows_per_rank, w) gathered bands -> (h, w) frame (drops the padding rows)."""
+    world, _n, w = gathered.shape
+    frame = torch.empty((h, w), dtype=gathered.dtype, device=gathered.device)
+    for r in range(world):
+        rows = owned_rows(r, world, h, band_rows)
+        if len(rows):
+            frame[torch.as_tensor(rows, device=gathered.device)] = gathered[r, : len(rows)]
+    return frame
+
+
+def broadcast_scene(dist, ctx, rank, device):
+    """Rank 0 has uploaded the scene: broadcast its packed blob as ONE buffer and adopt it everywhere.
+    Returns the tensor that owns the blob on this rank (keep it alive as long as the context uses it)."""
+    meta = [ctx.scene_blob()[1] if rank == 0 else 0]
+    dist.broadcast_object_list(meta, src=0)
+    blob = torch.empty(meta[0], dtype=torch.uint8, device=device)
+    if rank == 0:
+        ctx.copy_scene_blob(blob, blob.numel())
+    dist.broadcast(blob, src=0)
+    ctx.adopt_scene_blob(blob.data_ptr(), blob.numel())
+    return blob
