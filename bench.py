@@ -42,6 +42,7 @@ def frame_size(n_gpus):
 def build_scene():
     import rtb200
 
+    rtb200.hostlib.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1; only rank 0 builds
     t0 = time.time()
     mesh = rtb200.Mesh().terrain(TERRAIN_QUADS, 100.0).finish(diffuse=(0.7, 0.7, 0.7))
     arrays = mesh.arrays()

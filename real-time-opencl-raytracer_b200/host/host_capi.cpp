@@ -4,6 +4,9 @@
 // modified or freed. No GPU code here; the device boundary is include/rtb200.h.
 #include <cstring>
 #include <new>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "BVH_Cuda.h"
 #include "Camera.h"
@@ -13,6 +16,22 @@
 #include "SplitBVHBuilder.h"
 
 extern "C" {
+
+// Threads used by the task-parallel SBVH builder (torchrun exports OMP_NUM_THREADS=1 to its workers).
+void rth_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int rth_get_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 
 void* rth_mesh_new() { return new (std::nothrow) Mesh(); }
 void rth_mesh_free(void* m) { delete (Mesh*)m; }

@@ -41,6 +41,11 @@ def lib():
     return _lib
 
 
+def set_num_threads(n):
+    """threads for the SBVH builder (OpenMP tasks); torchrun workers start with OMP_NUM_THREADS=1"""
+    lib().rth_set_num_threads(int(n))
+
+
 def _view(ptr, shape, dtype):
     n = int(np.prod(shape))
     if n == 0 or not ptr:
