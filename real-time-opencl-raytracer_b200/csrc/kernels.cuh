@@ -37,6 +37,12 @@ struct TraceArgs {
     unsigned long long* work_counter;  // persistent-warp work queue head (zeroed before launch)
 };
 
+#ifndef RTB_MINB_BATCH
+#define RTB_MINB_BATCH 1
+#endif
+#ifndef RTB_MINB_LANES
+#define RTB_MINB_LANES 1
+#endif
 static constexpr int kBlockThreads = 128;
 static constexpr int kWarpsPerBlock = kBlockThreads / 32;
 
@@ -80,7 +86,7 @@ __device__ __forceinline__ void store_ray(float4* rays_out, long long i, const R
 // Grid = (resident blocks per SM) x 148 SMs; every warp pulls 32-ray batches from a global queue
 // head with one atomicAdd by lane 0 + a shuffle, until the queue is empty.
 template <int SRC, bool ANY_HIT, bool SMEM_TOP>
-__global__ void __launch_bounds__(kBlockThreads) trace_kernel(const TraceArgs a, int smem_count) {
+__global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(const TraceArgs a, int smem_count) {
     extern __shared__ float4 smem_pairs[];
     if (SMEM_TOP) {
         for (int i = threadIdx.x; i < smem_count * 4; i += blockDim.x) smem_pairs[i] = a.scene.pairs[i];

@@ -17,10 +17,10 @@
 
 namespace rtb {
 
-static constexpr int kLaneChunk = 128;  // work items a warp takes from the global queue per atomicAdd
+static constexpr int kLaneChunk = 32;   // work items a warp takes from the global queue per atomicAdd
 
 template <int SRC, bool ANY_HIT>
-__global__ void __launch_bounds__(kBlockThreads) trace_lanes_kernel(const TraceArgs a, int refill_threshold, int inner_exit_threshold) {
+__global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_kernel(const TraceArgs a, int refill_threshold, int inner_exit_threshold) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;

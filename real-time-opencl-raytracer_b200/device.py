@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librtb200.so")
+LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "csrc", "librtb200.so")  # env override: kernel-variant experiments
 _lib = None
 
 CLOSEST, ANY = 0, 1
