@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--nccl-gather", action="store_true", help="N>1: gather the framebuffer with NCCL all_gather instead of peer stores")
     ap.add_argument("--extra", action="store_true", help="also time shadow / diffuse / frame passes (N=1)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -221,10 +222,28 @@ def main():
         band_idx = tiling.band_index(rank, world, h, BAND_ROWS, device="cuda")
         d_band = torch.empty((rows_per_rank, w), dtype=torch.int32, device="cuda")
         d_gather = torch.empty((world, rows_per_rank, w), dtype=torch.int32, device="cuda")
+        # preferred: gather fused into the kernel's store (peer-mapped framebuffer on rank 0, NVLink);
+        # fallback if CUDA IPC is unavailable: band pack + NCCL all_gather
+        shared_frame = None
+        if not args.nccl_gather:
+            try:
+                shared_frame = tiling.open_shared_frame(dist, ctx, rank, n_pix * 4)
+            except Exception as exc:  # noqa: BLE001
+                shared_frame = None
+                if rank == 0:
+                    print(f"bench: CUDA IPC framebuffer unavailable ({exc}); using NCCL all_gather", file=sys.stderr)
+            flag = torch.tensor([1 if shared_frame else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if not int(flag.item()):
+                shared_frame = None
     else:
         owned_rows = list(range(h))
+        shared_frame = None
 
     def step():
+        if shared_frame:
+            ctx.primary_gather_device(w, h, d_hits, shared_frame, part=rank, n_parts=world, band_rows=BAND_ROWS)
+            return
         ctx.primary_device(w, h, d_hits, None, part=rank, n_parts=world, band_rows=BAND_ROWS)
         if world > 1:
             with torch.cuda.stream(stream):
@@ -263,7 +282,7 @@ def main():
         torch.cuda.synchronize()
         step_ms.append(e0.elapsed_time(e1))
     barrier()
-    launches = ctx.counters()["kernel_launches"] + (args.steps if world > 1 else 0)  # + our band-pack copy per step
+    launches = ctx.counters()["kernel_launches"]
     total_ms = float(np.sum(step_ms))
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -298,21 +317,27 @@ def main():
         ctx.set_stream(stream.cuda_stream)
     else:
         # N > 1: params from host each step, own bands traced, framebuffer gathered, rank 0 reads the frame back
-        host_frame = torch.empty((world, rows_per_rank, w), dtype=torch.int32).pin_memory()
+        host_frame = (torch.empty((h, w), dtype=torch.int32) if shared_frame else torch.empty((world, rows_per_rank, w), dtype=torch.int32)).pin_memory()
+        done = torch.zeros(1, device="cuda")
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             ctx.set_params(params)
             with torch.cuda.stream(stream):
                 step()
-                if rank == 0:
+                if shared_frame:
+                    dist.all_reduce(done)  # frame-complete signal: every rank's stores have landed on rank 0
+                    if rank == 0:
+                        ctx.memcpy_to_host(host_frame, shared_frame, n_pix * 4)
+                elif rank == 0:
                     host_frame.copy_(d_gather, non_blocking=True)
             stream.synchronize()
         barrier()
         t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": rays_total * args.steps / float(t.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 128 * world,
-               "d2h_bytes_per_step": int(host_frame.numel() * 4), "call": "rt_set_params + rt_primary_device(bands) + NCCL all_gather + frame D2H on rank 0"}
+               "d2h_bytes_per_step": int(host_frame.numel() * 4), "call": ("rt_set_params + rt_primary_gather_device(bands, peer-mapped frame on rank 0) + 1-element all_reduce + frame D2H on rank 0"
+                        if shared_frame else "rt_set_params + rt_primary_device(bands) + NCCL all_gather + frame D2H on rank 0")}
 
     # clocks: the sampling window covers the K timed steps and the e2e loop; if the timed steps were shorter than
     # two sampling periods, extend the window with more (untimed) steps of the same load
@@ -355,7 +380,8 @@ def main():
             "config": {"workload": f"{w}x{h} primary rays ({rays_total} traversed/step) vs 999698-triangle displaced-grid terrain, SBVH via SplitBVHBuilder "
                                    f"(BASELINE configs[1]{'' if world == 1 else '; frame scaled with N at 16:9, interleaved 16-row bands, NCCL scene broadcast + framebuffer all_gather'})",
                        "frame": [w, h], "rays_per_step": rays_total, "l2": "not flushed" if args.no_flush else "flushed between timed steps (256 MiB fill)",
-                       "scene_build_s": build_s, "scene_broadcast_ms": bcast_ms, "band_rows": BAND_ROWS},
+                       "scene_build_s": build_s, "scene_broadcast_ms": bcast_ms, "band_rows": BAND_ROWS,
+                       "gather": "n/a (1 GPU)" if world == 1 else ("fused into the kernel store: peer-mapped framebuffer on rank 0 over NVLink (CUDA IPC)" if shared_frame else "NCCL all_gather of 4-byte/pixel bands")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         }
         if roof:
@@ -366,6 +392,8 @@ def main():
             line["extra"] = extra_passes(ctx, torch, rtb200, w, h, stream)
         print(json.dumps(line))
     if world > 1:
+        if shared_frame:
+            tiling.close_shared_frame(dist, ctx, rank, shared_frame)
         dist.barrier()
         dist.destroy_process_group()
 

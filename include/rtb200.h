@@ -124,6 +124,19 @@ int rt_trace_device(rt_context* ctx, int mode, int64_t n, const rt_ray* d_rays, 
  * untouched rows are left as they are. */
 int rt_primary_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
                       rt_ray* d_rays_out);
+/* Same primary pass with the gather fused into the store: besides (or instead of, d_hits may be NULL) the
+ * 16-byte hit records, every pixel's hit index (3 * triangle id or -1) is written to d_idx_frame[y*w+x].
+ * d_idx_frame may live on ANOTHER GPU (a peer mapping obtained with rt_ipc_open): each rank then stores its
+ * bands straight into rank 0's framebuffer over NVLink and no separate gather collective is needed. */
+int rt_primary_gather_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
+                             int32_t* d_idx_frame);
+/* Peer-visible device buffer across processes of one node (CUDA IPC): the owner allocates and passes the
+ * 64-byte handle to its peers (any transport), they map it. */
+int rt_ipc_alloc(rt_context* ctx, size_t bytes, void** out_device_ptr, unsigned char out_handle[64]);
+int rt_ipc_open(rt_context* ctx, const unsigned char handle[64], void** out_device_ptr);
+int rt_ipc_close(rt_context* ctx, void* device_ptr);
+int rt_ipc_free(rt_context* ctx, void* device_ptr);
+int rt_memcpy_to_host(rt_context* ctx, void* dst_host, const void* src_device, size_t bytes);
 /* Shadow rays built in-kernel from rays + their closest hits exactly as vR.cl:1314,1407-1441 and
  * traced any-hit. Entries whose hit idx < 0 produce idx = -1, t = RT_T_INIT. d_shadow_rays_out may
  * be NULL. */

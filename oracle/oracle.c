@@ -225,6 +225,60 @@ static void trace_impl(const orc_scene* s, int mode, int64_t n, const float* ray
     if (counters) { counters[0] = ci; counters[1] = cl; counters[2] = ct; counters[3] = cm; }
 }
 
+/* per-ray operation trace for scheduler studies (tools/simsched.c): seg[i*max_seg + 2k] = inner visits before the
+ * k-th leaf, seg[i*max_seg + 2k+1] = triangle tests in that leaf; nseg[i] = entries used (a trailing run of inner
+ * visits with no leaf after it is stored with tri count 0). closest-hit only. */
+void orc_trace_segments(const orc_scene* s, int64_t n, const float* rays, uint16_t* seg, int max_seg, int* nseg) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; i++) {
+        const float* r8 = rays + i * 8;
+        Ray ray;
+        ray.ori = mk3(r8[0], r8[1], r8[2]);
+        ray.dir = mk3(r8[4], r8[5], r8[6]);
+        float tHit = r8[3];
+        uint16_t* out = seg + (size_t)i * max_seg;
+        int ns = 0, run = 0;
+        int stack[STACK_SIZE], count = 1;
+        stack[0] = 0;
+        while (count > 0) {
+            int node = stack[count - 1];
+            const int* row2 = (const int*)(s->nodes + (size_t)node * 12 + 8);
+            int l = row2[0];
+            if (l >= 0) {
+                int r = row2[1];
+                run++;
+                float a0, a1, b0, b1;
+                ray_box(&ray, s->nodes + (size_t)l * 12, s->nodes + (size_t)l * 12 + 4, &a0, &a1);
+                ray_box(&ray, s->nodes + (size_t)r * 12, s->nodes + (size_t)r * 12 + 4, &b0, &b1);
+                int h0 = (a0 <= a1) && (a1 >= TMIN) && (a0 <= tHit), h1 = (b0 <= b1) && (b1 >= TMIN) && (b0 <= tHit);
+                if (h0 && h1) {
+                    if (a0 > b0) { int t = l; l = r; r = t; }
+                    stack[count - 1] = r;
+                    stack[count++] = l;
+                } else if (h0) stack[count - 1] = l;
+                else if (h1) stack[count - 1] = r;
+                else --count;
+            } else {
+                int off = row2[2], cnt = row2[3];
+                for (int k = 0; k < cnt; k++) {
+                    int tri1 = s->tri_indices[off + k];
+                    f3 v0 = ld3(s->verts + (size_t)s->indices[tri1] * 4);
+                    f3 e1 = sub3(ld3(s->verts + (size_t)s->indices[tri1 + 1] * 4), v0);
+                    f3 e2 = sub3(ld3(s->verts + (size_t)s->indices[tri1 + 2] * 4), v0);
+                    float u, v;
+                    float t = RayTriangleIntersection(&ray, v0, e1, e2, &u, &v);
+                    if (t < tHit && t > TMIN) tHit = t;
+                }
+                if (ns + 2 <= max_seg) { out[ns++] = (uint16_t)run; out[ns++] = (uint16_t)cnt; }
+                run = 0;
+                --count;
+            }
+        }
+        if (run && ns + 2 <= max_seg) { out[ns++] = (uint16_t)run; out[ns++] = 0; }
+        nseg[i] = ns;
+    }
+}
+
 /* per-ray visit counts (inner, leaf, tris) for workload analysis: stats[3*i + {0,1,2}] */
 void orc_trace_stats(const orc_scene* s, int mode, int64_t n, const float* rays, void* hits_v, uint32_t* stats) {
     Hit* hits = (Hit*)hits_v;

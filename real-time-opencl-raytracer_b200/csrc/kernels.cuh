@@ -34,6 +34,8 @@ struct TraceArgs {
     float4* hits_out;         // 1 x float4 per ray {bits(idx), t, u, v}
     float4* rays_out;         // optional: the generated rays (SRC_PRIMARY, SRC_SHADOW)
     unsigned int* frame_out;  // render kernel only
+    int* idx_frame_out;       // optional (SRC_PRIMARY): 4-byte/pixel hit-index framebuffer; may be a PEER GPU's memory
+                              // (store-fused gather over NVLink: the pixel goes straight into the gathered frame)
     unsigned long long* work_counter;  // persistent-warp work queue head (zeroed before launch)
 };
 
@@ -120,7 +122,10 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
                 out_index = (long long)y * a.w + x;
                 active = primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray);
                 if (a.rays_out) store_ray(a.rays_out, out_index, ray);
-                if (!active) a.hits_out[out_index] = make_float4(__int_as_float(-1), RTB_T_INIT, 0.0f, 0.0f);
+                if (!active) {
+                    if (a.hits_out) a.hits_out[out_index] = make_float4(__int_as_float(-1), RTB_T_INIT, 0.0f, 0.0f);
+                    if (a.idx_frame_out) a.idx_frame_out[out_index] = -1;
+                }
             }
         } else {  // SRC_SHADOW
             const long long i = (long long)batch * 32 + lane;
@@ -147,7 +152,8 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
         }
         if (active) {
             const TraceResult r = traverse<ANY_HIT, SMEM_TOP>(a.scene, smem_pairs, smem_count, ray, tmax);
-            a.hits_out[out_index] = make_float4(__int_as_float(r.idx), r.t, r.u, r.v);
+            if (SRC != SRC_PRIMARY || a.hits_out) a.hits_out[out_index] = make_float4(__int_as_float(r.idx), r.t, r.u, r.v);
+            if (SRC == SRC_PRIMARY && a.idx_frame_out) a.idx_frame_out[out_index] = r.idx;
         }
     }
 }

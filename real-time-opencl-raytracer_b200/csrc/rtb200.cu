@@ -409,11 +409,11 @@ extern "C" int rt_trace(rt_context* ctx, int mode, int64_t n, const rt_ray* rays
     return RT_OK;
 }
 
-extern "C" int rt_primary_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
-                                 rt_ray* d_rays_out) {
+static int primary_impl(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits, rt_ray* d_rays_out,
+                        int32_t* d_idx_frame) {
     int rc = require(ctx, true, false);
     if (rc) return rc;
-    if (!d_hits) return set_err(ctx, RT_E_INVALID, "rt_primary_device: d_hits is NULL");
+    if (!d_hits && !d_idx_frame) return set_err(ctx, RT_E_INVALID, "primary pass: no output buffer given");
     CK(ctx, cudaSetDevice(ctx->device));
     TraceArgs a;
     memset(&a, 0, sizeof a);
@@ -422,14 +422,72 @@ extern "C" int rt_primary_device(rt_context* ctx, int w, int h, int part, int n_
     if ((rc = band_setup(ctx, a, w, h, part, n_parts, band_rows))) return rc;
     a.hits_out = (float4*)d_hits;
     a.rays_out = (float4*)d_rays_out;
+    a.idx_frame_out = d_idx_frame;
     const int st = smem_top_count(ctx);
-    if (ctx->opt_scheduler == 1 && !st)
+    if (ctx->opt_scheduler == 1 && !st && d_hits && !d_idx_frame)
         rc = launch_lanes(ctx, trace_lanes_kernel<SRC_PRIMARY, false>, a, a.num_batches * 32);
     else
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, true>, a, st)
                 : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0);
     if (rc == RT_OK) ctx->counters[RT_CNT_RAYS_TRACED] += (uint64_t)a.num_batches * 32;
     return rc;
+}
+
+extern "C" int rt_primary_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
+                                 rt_ray* d_rays_out) {
+    if (ctx && !d_hits) return set_err(ctx, RT_E_INVALID, "rt_primary_device: d_hits is NULL");
+    return primary_impl(ctx, w, h, part, n_parts, band_rows, d_hits, d_rays_out, nullptr);
+}
+
+extern "C" int rt_primary_gather_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
+                                        int32_t* d_idx_frame) {
+    return primary_impl(ctx, w, h, part, n_parts, band_rows, d_hits, nullptr, d_idx_frame);
+}
+
+// ---- peer-visible framebuffer (CUDA IPC): one process per GPU, rank 0 owns the frame, the others map it ----
+extern "C" int rt_ipc_alloc(rt_context* ctx, size_t bytes, void** out_device_ptr, unsigned char out_handle[64]) {
+    if (!ctx || !out_device_ptr || !out_handle || !bytes) return RT_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    CK(ctx, cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    CK(ctx, cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return set_err(ctx, RT_E_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(out_handle, &h, 64);
+    *out_device_ptr = p;
+    return RT_OK;
+}
+extern "C" int rt_ipc_open(rt_context* ctx, const unsigned char handle[64], void** out_device_ptr) {
+    if (!ctx || !handle || !out_device_ptr) return RT_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(ctx, cudaIpcOpenMemHandle(out_device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RT_OK;
+}
+extern "C" int rt_ipc_close(rt_context* ctx, void* device_ptr) {
+    if (!ctx || !device_ptr) return RT_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaIpcCloseMemHandle(device_ptr));
+    return RT_OK;
+}
+extern "C" int rt_ipc_free(rt_context* ctx, void* device_ptr) {
+    if (!ctx || !device_ptr) return RT_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaFree(device_ptr));
+    return RT_OK;
+}
+extern "C" int rt_memcpy_to_host(rt_context* ctx, void* dst_host, const void* src_device, size_t bytes) {
+    if (!ctx || !dst_host || !src_device) return RT_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->counters[RT_CNT_D2H_BYTES] += bytes;
+    return RT_OK;
 }
 
 // Host-buffer primary pass: the frame is cut into up to 8 contiguous row chunks; chunk c is traced on

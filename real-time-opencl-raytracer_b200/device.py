@@ -20,7 +20,8 @@ HIT_DTYPE = np.dtype([("idx", np.int32), ("t", np.float32), ("u", np.float32), (
 ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_version", "rt_set_stream", "rt_synchronize", "rt_upload_scene",
     "rt_scene_blob", "rt_copy_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_primary", "rt_trace_device",
-    "rt_primary_device", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
+    "rt_primary_device", "rt_primary_gather_device", "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free",
+    "rt_memcpy_to_host", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
     "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest",
 ]
 
@@ -54,6 +55,12 @@ def lib():
         L.rt_primary.argtypes = [vp, i32, i32, vp]
         L.rt_primary_device.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
         L.rt_shadow_device.argtypes = [vp, i64, vp, vp, vp, vp]
+        L.rt_primary_gather_device.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
+        L.rt_ipc_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p]
+        L.rt_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+        L.rt_ipc_close.argtypes = [vp, vp]
+        L.rt_ipc_free.argtypes = [vp, vp]
+        L.rt_memcpy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
         L.rt_diffuse_rays_device.argtypes = [vp, i64, vp, vp, i32, C.c_uint32, vp, vp]
         L.rt_render_frame_device.argtypes = [vp, i32, i32, i32, i32, i32, vp]
         L.rt_get_counters.argtypes = [vp, vp]
@@ -196,6 +203,29 @@ class Context:
 
     def primary_device(self, w, h, d_hits, d_rays_out=None, part=0, n_parts=1, band_rows=4):
         self._ck(lib().rt_primary_device(self._h, w, h, part, n_parts, band_rows, _ptr(d_hits), _ptr(d_rays_out)))
+
+    def primary_gather_device(self, w, h, d_hits, d_idx_frame, part=0, n_parts=1, band_rows=4):
+        """primary pass that also (or only) stores the 4-byte hit index per pixel into `d_idx_frame` (may be peer memory)"""
+        self._ck(lib().rt_primary_gather_device(self._h, w, h, part, n_parts, band_rows, _ptr(d_hits), _ptr(d_idx_frame)))
+
+    def ipc_alloc(self, nbytes):
+        p, handle = C.c_void_p(), C.create_string_buffer(64)
+        self._ck(lib().rt_ipc_alloc(self._h, nbytes, C.byref(p), handle))
+        return p.value, handle.raw
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        self._ck(lib().rt_ipc_open(self._h, handle, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._ck(lib().rt_ipc_close(self._h, ptr))
+
+    def ipc_free(self, ptr):
+        self._ck(lib().rt_ipc_free(self._h, ptr))
+
+    def memcpy_to_host(self, dst, src_ptr, nbytes):
+        self._ck(lib().rt_memcpy_to_host(self._h, _ptr(dst), src_ptr, nbytes))
 
     def shadow_device(self, n, d_rays, d_hits, d_shadow_hits, d_shadow_rays_out=None):
         self._ck(lib().rt_shadow_device(self._h, n, _ptr(d_rays), _ptr(d_hits), _ptr(d_shadow_hits), _ptr(d_shadow_rays_out)))

@@ -65,3 +65,26 @@ def broadcast_scene(dist, ctx, rank, device):
     dist.broadcast(blob, src=0)
     ctx.adopt_scene_blob(blob.data_ptr(), blob.numel())
     return blob
+
+
+def open_shared_frame(dist, ctx, rank, nbytes):
+    """Store-fused gather: rank 0 allocates the framebuffer, every other rank maps it through CUDA IPC and its
+    trace kernel writes pixels straight into it over NVLink (rt_primary_gather_device). Returns the device
+    pointer valid on THIS rank; release with close_shared_frame."""
+    box = [None]
+    ptr = None
+    if rank == 0:
+        ptr, handle = ctx.ipc_alloc(nbytes)
+        box = [handle]
+    dist.broadcast_object_list(box, src=0)
+    if rank != 0:
+        ptr = ctx.ipc_open(box[0])
+    return ptr
+
+
+def close_shared_frame(dist, ctx, rank, ptr):
+    dist.barrier()
+    if rank == 0:
+        ctx.ipc_free(ptr)
+    else:
+        ctx.ipc_close(ptr)

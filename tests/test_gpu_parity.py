@@ -182,6 +182,35 @@ def test_band_partition_covers_frame(ctx):
         assert torch.equal(img, img_whole)
 
 
+def test_fused_gather_store_matches_hits(ctx):
+    """rt_primary_gather_device: the 4-byte/pixel index frame (the store-fused gather target; here a local IPC-capable
+    allocation) equals the idx field of the hit records, for whole frames and for band partitions, with and without hits"""
+    import torch
+
+    g = load_scene("mix")
+    _upload(ctx, g)
+    w, h = 96, 64
+    hits = torch.zeros((w * h, 4), device="cuda")
+    ctx.primary_device(w, h, hits)
+    ctx.synchronize()
+    want = hits.view(torch.int32)[:, 0].cpu().numpy()
+    ptr, handle = ctx.ipc_alloc(w * h * 4)
+    assert len(handle) == 64
+    try:
+        for n_parts, band, with_hits in ((1, 4, True), (2, 16, True), (4, 8, False)):
+            got = np.full(w * h, 12345, dtype=np.int32)
+            hits2 = torch.zeros((w * h, 4), device="cuda") if with_hits else None
+            for part in range(n_parts):
+                ctx.primary_gather_device(w, h, hits2, ptr, part=part, n_parts=n_parts, band_rows=band)
+            ctx.synchronize()
+            ctx.memcpy_to_host(got, ptr, w * h * 4)
+            assert np.array_equal(got, want)
+            if with_hits:
+                assert torch.equal(hits2.view(torch.int32), hits.view(torch.int32))
+    finally:
+        ctx.ipc_free(ptr)
+
+
 def test_ragged_and_edge_inputs(ctx):
     g = load_scene("ico2")
     _upload(ctx, g)
