@@ -28,6 +28,8 @@ struct TraceArgs {
     int part, n_parts;        // SRC_PRIMARY: interleaved row bands, this rank's share
     int band_tile_rows;       // band_rows / 4
     long long num_batches;    // warp-sized work items
+    int tile_order;           // SRC_PRIMARY: 0 row-major tiles, 1 reversed, 2 multiplicative permutation, 3 permuted 64-tile chunks
+    unsigned int order_mul;   // odd multiplier coprime to the permuted count (host-chosen)
     // buffers
     const float4* rays_in;    // SRC_BUFFER, SRC_SHADOW (2 x float4 per ray)
     const float4* hits_in;    // SRC_SHADOW (closest hits of rays_in)
@@ -71,6 +73,13 @@ __device__ __forceinline__ Ray shadow_ray(f3 light_pos, const Ray& r, float t, f
 
 // Map a primary-ray batch (one warp = one 8x4 pixel tile) to pixel coordinates.
 __device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, int lane, int& x, int& y) {
+    if (a.tile_order == 1) batch = a.num_batches - 1 - batch;
+    else if (a.tile_order == 2) batch = (long long)(((unsigned long long)batch * a.order_mul) % (unsigned long long)a.num_batches);
+    else if (a.tile_order == 3) {
+        const long long chunks = a.num_batches >> 6;  // whole 64-tile chunks are permuted, the remainder stays in place
+        const long long c = batch >> 6;
+        if (c < chunks) batch = (long long)(((unsigned long long)c * a.order_mul) % (unsigned long long)chunks) * 64 + (batch & 63);
+    }
     const int tx = (int)(batch % a.tiles_x);
     const long long k = batch / a.tiles_x;  // index among this rank's tile rows
     const long long band = (long long)a.part + (k / a.band_tile_rows) * a.n_parts;

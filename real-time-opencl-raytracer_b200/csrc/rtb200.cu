@@ -56,6 +56,8 @@ struct rt_context {
                                 // -1 = auto: batch for in-kernel camera/shadow rays (coherent), lanes for ray buffers
     int opt_refill = 16;         // persistent lanes: refill when this many lanes are empty
     int opt_inner_exit = 8;     // persistent lanes: leave the inner phase when fewer lanes than this still descend
+    int opt_tile_order = 0;     // primary-ray tile order (see TraceArgs::tile_order)
+    int opt_zero_copy = 1;      // rt_primary: store hits directly into pinned host memory when the destination is pinned
     int opt_exact_div = 0;      // 1 = always use the compiler's full division in the box test
     uint64_t counters[RT_CNT_COUNT] = {0};
     std::string err;
@@ -245,6 +247,8 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     else if (!strcmp(name, "scheduler")) ctx->opt_scheduler = value < 0 ? -1 : (value ? 1 : 0);
     else if (!strcmp(name, "refill")) ctx->opt_refill = value < 1 ? 1 : (value > 32 ? 32 : value);
     else if (!strcmp(name, "inner_exit")) ctx->opt_inner_exit = value < 0 ? 0 : (value > 32 ? 32 : value);
+    else if (!strcmp(name, "tile_order")) ctx->opt_tile_order = value < 0 ? 0 : value;
+    else if (!strcmp(name, "zero_copy")) ctx->opt_zero_copy = value ? 1 : 0;
     else if (!strcmp(name, "exact_div")) {
         ctx->opt_exact_div = value ? 1 : 0;
         if (ctx->have_scene) ctx->view.coords_in_window = ctx->opt_exact_div ? 0 : ctx->hdr.coords_in_window;
@@ -345,6 +349,14 @@ static int band_setup(rt_context* ctx, TraceArgs& a, int w, int h, int part, int
     const long long bands = ((long long)h + band_rows - 1) / band_rows;
     const long long owned = bands > part ? (bands - part + n_parts - 1) / n_parts : 0;
     a.num_batches = owned * a.band_tile_rows * a.tiles_x;
+    a.tile_order = ctx->opt_tile_order;
+    {   // an odd multiplier near 0.618 * count that is coprime to the count being permuted
+        const unsigned long long cnt = a.tile_order == 3 ? (unsigned long long)(a.num_batches >> 6) : (unsigned long long)a.num_batches;
+        unsigned long long m = (unsigned long long)(0.6180339887 * (double)cnt) | 1ull;
+        auto gcd = [](unsigned long long x, unsigned long long y) { while (y) { unsigned long long t = x % y; x = y; y = t; } return x; };
+        while (cnt > 1 && gcd(m, cnt) != 1) m += 2;
+        a.order_mul = (unsigned int)(m ? m : 1);
+    }
     return RT_OK;
 }
 
@@ -498,6 +510,20 @@ extern "C" int rt_primary(rt_context* ctx, int w, int h, rt_hit* hits_host) {
     if (!hits_host || w <= 0 || h <= 0) return set_err(ctx, RT_E_INVALID, "rt_primary: bad arguments");
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)w * h * sizeof(rt_hit);
+    // Pinned (page-locked) destination: let the kernel store the hit records straight into host memory over
+    // PCIe (zero copy) -- the transfer then overlaps the tracing completely and no staging copy exists.
+    if (ctx->opt_zero_copy) {
+        cudaPointerAttributes attr;
+        memset(&attr, 0, sizeof attr);
+        if (cudaPointerGetAttributes(&attr, hits_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+            if ((rc = rt_primary_device(ctx, w, h, 0, 1, 4, (rt_hit*)attr.devicePointer, nullptr))) return rc;
+            CK(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->counters[RT_CNT_H2D_BYTES] += sizeof(ParamsBlock);
+            ctx->counters[RT_CNT_D2H_BYTES] += bytes;
+            return RT_OK;
+        }
+        cudaGetLastError();  // pageable memory: not an error, fall through to the staged path
+    }
     if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, bytes))) return rc;
     int chunks = 8;
     int rows = (((h + chunks - 1) / chunks) + 3) & ~3;  // rows per chunk, multiple of the 4-row warp tile

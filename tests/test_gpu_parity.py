@@ -211,6 +211,69 @@ def test_fused_gather_store_matches_hits(ctx):
         ctx.ipc_free(ptr)
 
 
+def test_primary_host_entry_zero_copy_and_staged(ctx):
+    """rt_primary (host buffer out): pinned destination (kernel stores straight to host memory), pinned but staged,
+    and pageable destination all give the device result bit for bit"""
+    import torch
+
+    g = load_scene("mix")
+    _upload(ctx, g)
+    w, h = (int(v) for v in g["wh"])
+    dev = torch.zeros((w * h, 4), device="cuda")
+    ctx.primary_device(w, h, dev)
+    ctx.synchronize()
+    want = dev.cpu().view(torch.int32)
+    pinned = torch.zeros((w * h, 4)).pin_memory()
+    for zc in (1, 0):
+        ctx.set_option("zero_copy", zc)
+        pinned.zero_()
+        ctx.primary(w, h, pinned)
+        assert torch.equal(pinned.view(torch.int32), want)
+    ctx.set_option("zero_copy", 1)
+    pageable = ctx.primary(w, h)
+    assert np.array_equal(pageable.view(np.int32).reshape(-1, 4), want.numpy())
+    for tile_order in (1, 2, 3):  # work-item order is a scheduling choice only
+        ctx.set_option("tile_order", tile_order)
+        dev2 = torch.zeros((w * h, 4), device="cuda")
+        ctx.primary_device(w, h, dev2)
+        ctx.synchronize()
+        assert torch.equal(dev2.view(torch.int32).cpu(), want)
+    ctx.set_option("tile_order", 0)
+
+
+@pytest.mark.parametrize("scheduler", [0, 1])
+def test_both_schedulers_identical(ctx, scheduler):
+    """batch and persistent-lanes schedulers run the same per-ray operation sequence"""
+    import torch
+
+    g = load_scene("mix")
+    _upload(ctx, g)
+    ctx.set_option("scheduler", scheduler)
+    try:
+        for refill, iexit in ((16, 8), (1, 0), (32, 16)):
+            ctx.set_option("refill", refill)
+            ctx.set_option("inner_exit", iexit)
+            assert_hits_identical(ctx.trace(rtb200.CLOSEST, g["random_rays"]), g["random_hits_closest"].view(HIT).reshape(-1), "closest")
+            assert_hits_identical(ctx.trace(rtb200.ANY, g["random_rays"]), g["random_hits_any"].view(HIT).reshape(-1), "any")
+            w, h = (int(v) for v in g["wh"])
+            d_hits = torch.zeros((w * h, 4), device="cuda")
+            d_rays = torch.zeros((w * h, 8), device="cuda")
+            d_sh = torch.zeros((w * h, 4), device="cuda")
+            ctx.primary_device(w, h, d_hits, d_rays)
+            ctx.shadow_device(w * h, d_rays, d_hits, d_sh)
+            ctx.synchronize()
+            want = g["primary_hits"].view(HIT).reshape(-1).copy()
+            gate = g["primary_gate"].astype(bool)
+            want[~gate] = (-1, rtb200.T_INIT, 0, 0)
+            assert_hits_identical(d_hits.cpu().numpy().view(HIT).reshape(-1), want, "primary")
+            v = g["shadow_valid"].astype(bool) & gate
+            assert_hits_identical(d_sh.cpu().numpy().view(HIT).reshape(-1)[v], g["shadow_hits"].view(HIT).reshape(-1)[v], "shadow")
+    finally:
+        ctx.set_option("scheduler", -1)
+        ctx.set_option("refill", 16)
+        ctx.set_option("inner_exit", 8)
+
+
 def test_ragged_and_edge_inputs(ctx):
     g = load_scene("ico2")
     _upload(ctx, g)

@@ -57,8 +57,8 @@ def timeit(fn, iters=10):
 
 
 for cfg in configs:
-    for k in ("scheduler", "refill", "inner_exit", "blocks_per_sm", "exact_div"):
-        default = {"scheduler": -1, "refill": 16, "inner_exit": 8, "blocks_per_sm": 0, "exact_div": 0}[k]
+    for k in ("scheduler", "refill", "inner_exit", "blocks_per_sm", "exact_div", "tile_order"):
+        default = {"scheduler": -1, "refill": 16, "inner_exit": 8, "blocks_per_sm": 0, "exact_div": 0, "tile_order": 0}[k]
         ctx.set_option(k, int(cfg.get(k, default)))
     tp = timeit(lambda: ctx.primary_device(w, h, d_hits))
     ts = timeit(lambda: ctx.shadow_device(n, d_rays, ref_p, d_sh))
