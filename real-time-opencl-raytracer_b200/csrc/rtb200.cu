@@ -27,6 +27,8 @@ struct rt_context {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // device->host copies that overlap tracing (rt_primary)
     cudaEvent_t chunk_events[16] = {nullptr};
+    cudaStream_t out_stream = nullptr;    // device->host copies of rt_trace chunks
+    cudaEvent_t out_events[16] = {nullptr};
     // scene
     uint8_t* d_blob = nullptr;
     size_t blob_bytes = 0;
@@ -106,7 +108,9 @@ extern "C" int rt_create(int device_ordinal, rt_context** out_ctx) {
     CK(nullptr, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     CK(nullptr, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CK(nullptr, cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->chunk_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : ctx->out_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CK(nullptr, cudaMalloc(&ctx->d_counter, 256));
     memset(&ctx->hdr, 0, sizeof ctx->hdr);
     memset(&ctx->view, 0, sizeof ctx->view);
@@ -135,6 +139,9 @@ extern "C" int rt_destroy(rt_context* ctx) {
     cudaFree(ctx->d_offsets);
     for (auto& ev : ctx->chunk_events)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->out_events)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -403,6 +410,19 @@ static int ensure(rt_context* ctx, void** p, size_t* have, size_t need) {
     return RT_OK;
 }
 
+// Device alias of a pinned (page-locked) host buffer, or nullptr for pageable memory.
+static void* pinned_alias(const void* host_ptr) {
+    cudaPointerAttributes attr;
+    memset(&attr, 0, sizeof attr);
+    if (cudaPointerGetAttributes(&attr, host_ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        return attr.devicePointer;
+    cudaGetLastError();  // pageable memory is not an error
+    return nullptr;
+}
+
+// Host-buffer batch operator. The batch is cut into chunks: the upload of chunk c+1 (copy stream) overlaps the
+// tracing of chunk c (context stream), and results go either straight into pinned host memory (zero copy) or
+// through a third stream's device->host copies.
 extern "C" int rt_trace(rt_context* ctx, int mode, int64_t n, const rt_ray* rays_host, rt_hit* hits_host) {
     int rc = require(ctx, false, false);
     if (rc) return rc;
@@ -411,11 +431,29 @@ extern "C" int rt_trace(rt_context* ctx, int mode, int64_t n, const rt_ray* rays
     if (n == 0) return RT_OK;
     CK(ctx, cudaSetDevice(ctx->device));
     if ((rc = ensure(ctx, &ctx->d_stage_in, &ctx->stage_in_bytes, (size_t)n * sizeof(rt_ray)))) return rc;
-    if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, (size_t)n * sizeof(rt_hit)))) return rc;
-    CK(ctx, cudaMemcpyAsync(ctx->d_stage_in, rays_host, (size_t)n * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = do_trace_device(ctx, mode, n, (const rt_ray*)ctx->d_stage_in, (rt_hit*)ctx->d_stage_out))) return rc;
-    CK(ctx, cudaMemcpyAsync(hits_host, ctx->d_stage_out, (size_t)n * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    rt_hit* direct_out = ctx->opt_zero_copy ? (rt_hit*)pinned_alias(hits_host) : nullptr;
+    if (!direct_out && (rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, (size_t)n * sizeof(rt_hit)))) return rc;
+    const int64_t chunk_rays = 1 << 18;  // 8 MB of rays per chunk
+    int chunks = (int)((n + chunk_rays - 1) / chunk_rays);
+    if (chunks > 16) chunks = 16;
+    const int64_t per = (((n + chunks - 1) / chunks) + 31) & ~(int64_t)31;
+    for (int c = 0; c < chunks; c++) {
+        const int64_t lo = (int64_t)c * per, hi = lo + per < n ? lo + per : n;
+        if (lo >= hi) break;
+        const rt_ray* d_in = (const rt_ray*)ctx->d_stage_in + lo;
+        CK(ctx, cudaMemcpyAsync((void*)d_in, rays_host + lo, (size_t)(hi - lo) * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(ctx, cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
+        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[c], 0));
+        rt_hit* d_out = direct_out ? direct_out + lo : (rt_hit*)ctx->d_stage_out + lo;
+        if ((rc = do_trace_device(ctx, mode, hi - lo, d_in, d_out))) return rc;
+        if (!direct_out) {
+            CK(ctx, cudaEventRecord(ctx->out_events[c], ctx->stream));
+            CK(ctx, cudaStreamWaitEvent(ctx->out_stream, ctx->out_events[c], 0));
+            CK(ctx, cudaMemcpyAsync(hits_host + lo, d_out, (size_t)(hi - lo) * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->out_stream));
+        }
+    }
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!direct_out) CK(ctx, cudaStreamSynchronize(ctx->out_stream));
     ctx->counters[RT_CNT_H2D_BYTES] += (uint64_t)n * sizeof(rt_ray);
     ctx->counters[RT_CNT_D2H_BYTES] += (uint64_t)n * sizeof(rt_hit);
     return RT_OK;
@@ -513,16 +551,13 @@ extern "C" int rt_primary(rt_context* ctx, int w, int h, rt_hit* hits_host) {
     // Pinned (page-locked) destination: let the kernel store the hit records straight into host memory over
     // PCIe (zero copy) -- the transfer then overlaps the tracing completely and no staging copy exists.
     if (ctx->opt_zero_copy) {
-        cudaPointerAttributes attr;
-        memset(&attr, 0, sizeof attr);
-        if (cudaPointerGetAttributes(&attr, hits_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
-            if ((rc = rt_primary_device(ctx, w, h, 0, 1, 4, (rt_hit*)attr.devicePointer, nullptr))) return rc;
+        if (void* alias = pinned_alias(hits_host)) {
+            if ((rc = rt_primary_device(ctx, w, h, 0, 1, 4, (rt_hit*)alias, nullptr))) return rc;
             CK(ctx, cudaStreamSynchronize(ctx->stream));
             ctx->counters[RT_CNT_H2D_BYTES] += sizeof(ParamsBlock);
             ctx->counters[RT_CNT_D2H_BYTES] += bytes;
             return RT_OK;
         }
-        cudaGetLastError();  // pageable memory: not an error, fall through to the staged path
     }
     if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, bytes))) return rc;
     int chunks = 8;
@@ -625,9 +660,14 @@ extern "C" int rt_render_frame(rt_context* ctx, int w, int h, uint32_t* out_host
     if (!out_host || w <= 0 || h <= 0) return set_err(ctx, RT_E_INVALID, "rt_render_frame: bad arguments");
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)w * h * 4;
-    if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, bytes))) return rc;
-    if ((rc = rt_render_frame_device(ctx, w, h, 0, 1, 4, (uint32_t*)ctx->d_stage_out))) return rc;
-    CK(ctx, cudaMemcpyAsync(out_host, ctx->d_stage_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    void* alias = ctx->opt_zero_copy ? pinned_alias(out_host) : nullptr;
+    if (alias) {  // pinned destination: the kernel stores the pixels straight into host memory
+        if ((rc = rt_render_frame_device(ctx, w, h, 0, 1, 4, (uint32_t*)alias))) return rc;
+    } else {
+        if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, bytes))) return rc;
+        if ((rc = rt_render_frame_device(ctx, w, h, 0, 1, 4, (uint32_t*)ctx->d_stage_out))) return rc;
+        CK(ctx, cudaMemcpyAsync(out_host, ctx->d_stage_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->counters[RT_CNT_H2D_BYTES] += sizeof(ParamsBlock);
     ctx->counters[RT_CNT_D2H_BYTES] += bytes;

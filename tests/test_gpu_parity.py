@@ -241,6 +241,34 @@ def test_primary_host_entry_zero_copy_and_staged(ctx):
     ctx.set_option("tile_order", 0)
 
 
+def test_trace_host_pipeline_large_batch(ctx):
+    """rt_trace on a batch that spans several upload/trace/download chunks, pageable and pinned (zero-copy) buffers,
+    against rt_trace_device on the same rays; frame call with a pinned destination"""
+    import torch
+
+    g = load_scene("mix")
+    _upload(ctx, g)
+    reps = 300  # 2048 * 300 = 614 400 rays -> 3 chunks
+    rays = np.tile(g["random_rays"], (reps, 1))
+    rays[:, 0:3] += (np.arange(rays.shape[0], dtype=np.float32)[:, None] % 7) * 0.01
+    n = rays.shape[0]
+    d_r = torch.from_numpy(rays).cuda()
+    d_h = torch.zeros((n, 4), device="cuda")
+    for mode in (rtb200.CLOSEST, rtb200.ANY):
+        ctx.trace_device(mode, n, d_r, d_h)
+        ctx.synchronize()
+        want = d_h.cpu().view(torch.int32)
+        got = ctx.trace(mode, rays)  # pageable numpy in/out
+        assert np.array_equal(got.view(np.int32).reshape(-1, 4), want.numpy())
+        pr, ph = torch.from_numpy(rays).pin_memory(), torch.zeros((n, 4)).pin_memory()
+        ctx.trace(mode, pr, ph)  # pinned in, zero-copy out
+        assert torch.equal(ph.view(torch.int32), want)
+    w, h = (int(v) for v in g["wh"])
+    img_pinned = torch.zeros((h, w), dtype=torch.int32).pin_memory()
+    ctx.render_frame(w, h, img_pinned)
+    assert np.array_equal(img_pinned.numpy().view(np.uint32), ctx.render_frame(w, h))
+
+
 @pytest.mark.parametrize("scheduler", [0, 1])
 def test_both_schedulers_identical(ctx, scheduler):
     """batch and persistent-lanes schedulers run the same per-ray operation sequence"""
