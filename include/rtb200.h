@@ -160,8 +160,11 @@ int rt_set_option(rt_context* ctx, const char* name, int value);
 /* GPU self test of the box test's hoisted exact division against the compiler's IEEE division on
  * `samples` random operand pairs; *out_mismatches must come back 0. */
 int rt_selftest(rt_context* ctx, int64_t samples, uint32_t seed, uint64_t* out_mismatches);
-/* Scene statistics: [0] node pairs, [1] packed triangles, [2] blob bytes, [3] max tree depth */
-int rt_scene_info(rt_context* ctx, int64_t out[4]);
+/* Same comparison with the numerator's binary exponent fixed (probe of the admitted operand window). */
+int rt_selftest_range(rt_context* ctx, int64_t samples, uint32_t seed, int x_exponent, uint64_t* out_mismatches);
+/* Scene statistics: [0] node pairs, [1] packed triangles, [2] blob bytes, [3] max tree depth,
+ * [4] 1 if every box coordinate admits the hoisted exact division (else the full division is used), [5] BFS-ordered pairs */
+int rt_scene_info(rt_context* ctx, int64_t out[6]);
 
 #ifdef __cplusplus
 }

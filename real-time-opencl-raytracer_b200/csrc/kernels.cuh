@@ -358,7 +358,33 @@ __global__ void diffuse_rays_kernel(SceneView s, long long n, const float4* rays
 }
 
 // ---- self test: div_hoisted(x, d, div_prepare(d)) must equal x / d bit for bit over the admitted window ---
-// d: any sign, exponent in [-20, 20]; x: 0 or any sign, exponent in [-43, 21]; mantissas random or edge patterns.
+// d: any sign, exponent in [-20, 20]; x: 0 or any sign, exponent in [-100, 61]; mantissas random or edge patterns.
+// Range probe: same comparison with the numerator's exponent fixed to `ex` (unbiased) and the divisor's exponent
+// in [-20, 20]; used to establish how far below 1.0 the numerator may go before the hoisted sequence (which has no
+// FCHK guard) stops matching the compiler's guarded division.
+__global__ void selftest_division_range_kernel(unsigned int seed, int iters, int ex, unsigned long long* mismatches) {
+    const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int state = lowbias32(tid ^ (seed * 0x9e3779b9u));
+    unsigned long long bad = 0;
+    for (int i = 0; i < iters; i++) {
+        state = lowbias32(state + 0x6a09e667u);
+        const unsigned int a = state;
+        state = lowbias32(state + 0xbb67ae85u);
+        const unsigned int b = state;
+        state = lowbias32(state + 0x3c6ef372u);
+        const unsigned int c = state;
+        const unsigned int ed = 127u - 20u + (c % 40u);
+        const float d = __uint_as_float(((a >> 31) << 31) | (ed << 23) | (a & 0x7FFFFFu));
+        float x;
+        if (ex >= -126) x = __uint_as_float(((b >> 31) << 31) | ((unsigned int)(ex + 127) << 23) | (b & 0x7FFFFFu));
+        else x = __uint_as_float(((b >> 31) << 31) | ((b & 0x7FFFFFu) >> (-126 - ex)));  // denormal with top bit at 2^ex
+        const float want = x / d;
+        const float got = div_hoisted(x, d, div_prepare(d));
+        if (__float_as_uint(want) != __float_as_uint(got) && !(want == 0.0f && got == 0.0f)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 __global__ void selftest_division_kernel(unsigned int seed, int iters, unsigned long long* mismatches) {
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int state = lowbias32(tid ^ (seed * 0x9e3779b9u));
@@ -375,7 +401,7 @@ __global__ void selftest_division_kernel(unsigned int seed, int iters, unsigned 
         if ((c & 7u) == 0u) md = edge[(c >> 3) & 7u];
         if ((c & 0x38u) == 0u) mx = edge[(c >> 6) & 7u];
         const unsigned int ed = 127u - 20u + ((c >> 9) % 41u);   // exponent -20..20
-        const unsigned int ex = 127u - 43u + ((c >> 16) % 65u);  // exponent -43..21
+        const unsigned int ex = 127u - 100u + ((c >> 16) % 162u);  // exponent -100..61
         const float d = __uint_as_float(((a >> 31) << 31) | (ed << 23) | md);
         float x = __uint_as_float(((b >> 31) << 31) | (ex << 23) | mx);
         if ((c >> 24) == 0u) x = 0.0f;

@@ -62,6 +62,9 @@ struct rt_context {
     int opt_zero_copy = 1;      // rt_primary: store hits directly into pinned host memory when the destination is pinned
     int opt_exact_div = 0;      // 1 = always use the compiler's full division in the box test
     uint64_t counters[RT_CNT_COUNT] = {0};
+    // resident blocks per SM of each kernel (occupancy query is a slow host call: done once per kernel and smem size)
+    struct OccEntry { const void* fn; size_t smem; int per_sm; } occ_cache[32];
+    int occ_count = 0;
     std::string err;
 };
 
@@ -264,13 +267,15 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     return RT_OK;
 }
 
-extern "C" int rt_scene_info(rt_context* ctx, int64_t out[4]) {
+extern "C" int rt_scene_info(rt_context* ctx, int64_t out[6]) {
     if (!ctx || !out) return RT_E_INVALID;
     if (!ctx->have_scene) return set_err(ctx, RT_E_NO_SCENE, "rt_scene_info: no scene uploaded");
     out[0] = ctx->hdr.num_pairs;
     out[1] = ctx->hdr.num_tris;
     out[2] = (int64_t)ctx->blob_bytes;
     out[3] = ctx->hdr.max_depth;
+    out[4] = ctx->hdr.coords_in_window;
+    out[5] = ctx->hdr.top_pairs;
     return RT_OK;
 }
 
@@ -288,13 +293,29 @@ extern "C" int rt_reset_counters(rt_context* ctx) {
 // ---- launch helpers ------------------------------------------------------------------------------
 
 template <typename K>
+static int blocks_per_sm(rt_context* ctx, K kernel, size_t smem, int* out) {
+    for (int i = 0; i < ctx->occ_count; i++)
+        if (ctx->occ_cache[i].fn == (const void*)kernel && ctx->occ_cache[i].smem == smem) {
+            *out = ctx->occ_cache[i].per_sm;
+            return RT_OK;
+        }
+    if (smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (ctx->occ_count < 32) ctx->occ_cache[ctx->occ_count++] = {(const void*)kernel, smem, per_sm};
+    *out = per_sm;
+    return RT_OK;
+}
+
+template <typename K>
 static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, int smem_count) {
     const size_t smem = (size_t)smem_count * 64;
-    if (smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = ctx->opt_blocks_per_sm;
-    if (per_sm <= 0) {
-        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, smem));
-        if (per_sm < 1) per_sm = 1;
+    {
+        int occ = 1, rc = blocks_per_sm(ctx, kernel, smem, &occ);  // also raises the dynamic-smem limit once
+        if (rc) return rc;
+        if (per_sm <= 0) per_sm = occ;
     }
     long long blocks = (long long)per_sm * ctx->num_sms;
     const long long needed = (a.num_batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -312,8 +333,8 @@ template <typename K>
 static int launch_lanes(rt_context* ctx, K kernel, TraceArgs& a, long long total_items) {
     int per_sm = ctx->opt_blocks_per_sm;
     if (per_sm <= 0) {
-        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, 0));
-        if (per_sm < 1) per_sm = 1;
+        int rc = blocks_per_sm(ctx, kernel, 0, &per_sm);
+        if (rc) return rc;
     }
     long long blocks = (long long)per_sm * ctx->num_sms;
     const long long needed = (total_items + kBlockThreads - 1) / kBlockThreads;
@@ -684,6 +705,23 @@ extern "C" int rt_selftest(rt_context* ctx, int64_t samples, uint32_t seed, uint
     long long blocks = (samples + (long long)threads * iters - 1) / ((long long)threads * iters);
     if (blocks < 1) blocks = 1;
     selftest_division_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(seed, iters, ctx->d_counter + 8);
+    CK(ctx, cudaGetLastError());
+    unsigned long long bad = 0;
+    CK(ctx, cudaMemcpyAsync(&bad, ctx->d_counter + 8, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_mismatches = bad;
+    return RT_OK;
+}
+
+// Range probe of the hoisted division: numerator exponent fixed to `x_exponent` (unbiased, < -126 = denormal).
+extern "C" int rt_selftest_range(rt_context* ctx, int64_t samples, uint32_t seed, int x_exponent, uint64_t* out_mismatches) {
+    if (!ctx || !out_mismatches || samples < 1) return RT_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemsetAsync(ctx->d_counter + 8, 0, sizeof(unsigned long long), ctx->stream));
+    const int threads = 256, iters = 1024;
+    long long blocks = (samples + (long long)threads * iters - 1) / ((long long)threads * iters);
+    if (blocks < 1) blocks = 1;
+    selftest_division_range_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(seed, iters, x_exponent, ctx->d_counter + 8);
     CK(ctx, cudaGetLastError());
     unsigned long long bad = 0;
     CK(ctx, cudaMemcpyAsync(&bad, ctx->d_counter + 8, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));

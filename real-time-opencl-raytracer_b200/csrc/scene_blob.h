@@ -44,7 +44,7 @@ struct BlobHeader {
     int32_t max_depth;     // depth of the reference tree (root = 1)
     int32_t V, T, Vn, M;   // shading-array sizes (Vn = M = 0: no shading data)
     int32_t num_ref_nodes; // N of the reference array
-    int32_t coords_in_window;  // all pair-box coordinates are 0 or have magnitude in [2^-20, 2^20]
+    int32_t coords_in_window;  // all pair-box coordinates are 0 or have magnitude in [2^-77, 2^60]
     int32_t reserved0[1];
     uint64_t off_pairs, off_tris, off_verts, off_indices, off_normals, off_normal_indices, off_mat_diffuse,
         off_tri_to_material;

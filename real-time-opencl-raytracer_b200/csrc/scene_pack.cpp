@@ -152,7 +152,7 @@ int pack_scene(const SceneInputs& in, int top_pairs, uint8_t** out_blob, uint64_
     auto check = [&in_window](const float* c) {
         for (int k = 0; k < 3; k++) {
             const float a = c[k] < 0 ? -c[k] : c[k];
-            if (!(c[k] == 0.0f || (a >= 9.5367431640625e-07f && a <= 1048576.0f))) in_window = false;
+            if (!(c[k] == 0.0f || (a >= 6.617444900424222e-24f && a <= 1.152921504606847e18f))) in_window = false;  // device_math.cuh coord_in_window
         }
     };
     for (int p = 0; p < P; p++) {

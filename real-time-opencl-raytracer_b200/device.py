@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "rt_scene_blob", "rt_copy_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_primary", "rt_trace_device",
     "rt_primary_device", "rt_primary_gather_device", "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free",
     "rt_memcpy_to_host", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
-    "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest",
+    "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest", "rt_selftest_range",
 ]
 
 
@@ -68,6 +68,7 @@ def lib():
         L.rt_set_option.argtypes = [vp, C.c_char_p, i32]
         L.rt_scene_info.argtypes = [vp, vp]
         L.rt_selftest.argtypes = [vp, i64, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.rt_selftest_range.argtypes = [vp, i64, C.c_uint32, i32, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -137,10 +138,16 @@ class Context:
         self._ck(lib().rt_selftest(self._h, samples, seed, C.byref(bad)))
         return int(bad.value)
 
+    def selftest_range(self, samples, x_exponent, seed=1):
+        bad = C.c_uint64(0)
+        self._ck(lib().rt_selftest_range(self._h, samples, seed, x_exponent, C.byref(bad)))
+        return int(bad.value)
+
     def scene_info(self):
-        out = np.zeros(4, dtype=np.int64)
+        out = np.zeros(6, dtype=np.int64)
         self._ck(lib().rt_scene_info(self._h, out.ctypes.data))
-        return {"node_pairs": int(out[0]), "packed_tris": int(out[1]), "blob_bytes": int(out[2]), "max_depth": int(out[3])}
+        return {"node_pairs": int(out[0]), "packed_tris": int(out[1]), "blob_bytes": int(out[2]), "max_depth": int(out[3]),
+                "hoisted_division": bool(out[4]), "bfs_pairs": int(out[5])}
 
     # --- scene (reference initRayTrace buffers) ---
     def upload_scene(self, mesh, bvh_nodes, tri_indices, shading=True):

@@ -84,9 +84,26 @@ def test_render_frame_vs_golden(ctx, name):
 
 
 def test_hoisted_division_is_the_ieee_quotient(ctx):
-    """the box test's per-ray-hoisted division (FMUL + 2 FFMA) == `/` bit for bit on 2 G random operand pairs"""
+    """the box test's per-ray-hoisted division (FMUL + 2 FFMA) == `/` bit for bit on 2 G random operand pairs drawn
+    from the admitted window, and the window has margin: exact at numerator exponents -104 and +105 too"""
     for seed in (1, 2):
         assert ctx.selftest(1 << 30, seed) == 0
+    for ex in (-104, -100, -77, -20, 0, 61, 100, 105):
+        assert ctx.selftest_range(1 << 22, ex) == 0
+    assert ctx.selftest_range(1 << 22, -125) > 0  # and it does break outside: the guard is needed
+
+
+def test_scenes_with_tiny_coordinates_use_the_hoisted_path(ctx):
+    """icospheres contain coordinates like 1e-16 (and exact zeros): still inside the admitted window"""
+    for name in ("ico2", "mix", "terrain12"):
+        g = load_scene(name)
+        _upload(ctx, g)
+        assert ctx.scene_info()["hoisted_division"]
+    huge = load_scene("ico2")
+    nodes = huge["ref_nodes"].copy()
+    nodes[1, 4] = 1e30  # one child-box coordinate outside the window -> the whole scene falls back to the full division
+    ctx.upload_scene(mesh_dict(huge), nodes, huge["ref_tri_indices"])
+    assert not ctx.scene_info()["hoisted_division"]
 
 
 @pytest.mark.parametrize("exact_div", [0, 1])
