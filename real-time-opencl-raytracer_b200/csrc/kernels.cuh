@@ -96,7 +96,7 @@ __device__ __forceinline__ void store_ray(float4* rays_out, long long i, const R
 // ---- persistent-warp trace kernel ------------------------------------------------------------------
 // Grid = (resident blocks per SM) x 148 SMs; every warp pulls 32-ray batches from a global queue
 // head with one atomicAdd by lane 0 + a shuffle, until the queue is empty.
-template <int SRC, bool ANY_HIT, bool SMEM_TOP>
+template <int SRC, bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX = false>
 __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(const TraceArgs a, int smem_count) {
     extern __shared__ float4 smem_pairs[];
     if (SMEM_TOP) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
             }
         }
         if (active) {
-            const TraceResult r = traverse<ANY_HIT, SMEM_TOP>(a.scene, smem_pairs, smem_count, ray, tmax);
+            const TraceResult r = traverse<ANY_HIT, SMEM_TOP, FAST_BOX>(a.scene, smem_pairs, smem_count, ray, tmax);
             if (SRC != SRC_PRIMARY || a.hits_out) a.hits_out[out_index] = make_float4(__int_as_float(r.idx), r.t, r.u, r.v);
             if (SRC == SRC_PRIMARY && a.idx_frame_out) a.idx_frame_out[out_index] = r.idx;
         }

@@ -58,6 +58,7 @@ struct rt_context {
                                 // -1 = auto: batch for in-kernel camera/shadow rays (coherent), lanes for ray buffers
     int opt_refill = 16;         // persistent lanes: refill when this many lanes are empty
     int opt_inner_exit = 8;     // persistent lanes: leave the inner phase when fewer lanes than this still descend
+    int opt_fast_box = 0;       // 1 = approximate reciprocal/FMA box test for CLOSEST-hit batch kernels (NOT bit-exact; experiment)
     int opt_tile_order = 0;     // primary-ray tile order (see TraceArgs::tile_order)
     int opt_zero_copy = 1;      // rt_primary: store hits directly into pinned host memory when the destination is pinned
     int opt_exact_div = 0;      // 1 = always use the compiler's full division in the box test
@@ -257,6 +258,7 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     else if (!strcmp(name, "scheduler")) ctx->opt_scheduler = value < 0 ? -1 : (value ? 1 : 0);
     else if (!strcmp(name, "refill")) ctx->opt_refill = value < 1 ? 1 : (value > 32 ? 32 : value);
     else if (!strcmp(name, "inner_exit")) ctx->opt_inner_exit = value < 0 ? 0 : (value > 32 ? 32 : value);
+    else if (!strcmp(name, "fast_box")) ctx->opt_fast_box = value ? 1 : 0;
     else if (!strcmp(name, "tile_order")) ctx->opt_tile_order = value < 0 ? 0 : value;
     else if (!strcmp(name, "zero_copy")) ctx->opt_zero_copy = value ? 1 : 0;
     else if (!strcmp(name, "exact_div")) {
@@ -401,6 +403,8 @@ static int do_trace_device(rt_context* ctx, int mode, long long n, const rt_ray*
     if (ctx->opt_scheduler != 0 && !st)
         rc = mode == RT_CLOSEST ? launch_lanes(ctx, trace_lanes_kernel<SRC_BUFFER, false>, a, n)
                                 : launch_lanes(ctx, trace_lanes_kernel<SRC_BUFFER, true>, a, n);
+    else if (mode == RT_CLOSEST && ctx->opt_fast_box && !st)
+        rc = launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false, true>, a, 0);
     else if (mode == RT_CLOSEST)
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, true>, a, st)
                 : launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false>, a, 0);
@@ -497,6 +501,8 @@ static int primary_impl(rt_context* ctx, int w, int h, int part, int n_parts, in
     const int st = smem_top_count(ctx);
     if (ctx->opt_scheduler == 1 && !st && d_hits && !d_idx_frame)
         rc = launch_lanes(ctx, trace_lanes_kernel<SRC_PRIMARY, false>, a, a.num_batches * 32);
+    else if (ctx->opt_fast_box && !st)
+        rc = launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false, true>, a, 0);
     else
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, true>, a, st)
                 : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0);

@@ -43,10 +43,13 @@ struct TraceResult {
 };
 
 // Node fetch policy: TOP > 0 means pairs [0, TOP) are served from shared memory (`smem_pairs`).
-template <bool ANY_HIT, bool SMEM_TOP>
+template <bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX = false>
 __device__ __forceinline__ TraceResult traverse(const SceneView& s, const float4* __restrict__ smem_pairs, int smem_count,
                                                 const Ray& ray, float tHit) {
+    static_assert(!(ANY_HIT && FAST_BOX), "the approximate box test is for closest-hit only");
     const RayX rx = ray_prepare(ray, s.coords_in_window != 0);
+    RayF rf;
+    if (FAST_BOX) rf = ray_fast_prepare(ray);
     int stack[RTB_STACK];
     int sp = 0;
     int cur = s.root_ref;
@@ -67,7 +70,10 @@ __device__ __forceinline__ TraceResult traverse(const SceneView& s, const float4
                 q0 = __ldg(p); q1 = __ldg(p + 1); q2 = __ldg(p + 2); q3 = __ldg(p + 3);
             }
             float t0n, t0f, t1n, t1f;
-            if (rx.fast) {
+            if (FAST_BOX) {
+                ray_box_fast(rf, q0, q1, t0n, t0f);
+                ray_box_fast(rf, q2, q3, t1n, t1f);
+            } else if (rx.fast) {
                 ray_box_hoisted(rx, q0, q1, t0n, t0f);
                 ray_box_hoisted(rx, q2, q3, t1n, t1f);
             } else {
