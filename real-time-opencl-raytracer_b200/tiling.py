@@ -63,6 +63,9 @@ def broadcast_scene(dist, ctx, rank, device):
     if rank == 0:
         ctx.copy_scene_blob(blob, blob.numel())
     dist.broadcast(blob, src=0)
+    if blob.is_cuda:
+        # the collective runs on the framework's stream; the context reads the blob on its own stream
+        torch.cuda.synchronize(blob.device)
     ctx.adopt_scene_blob(blob.data_ptr(), blob.numel())
     return blob
 
