@@ -96,6 +96,14 @@ int rt_copy_scene_blob(rt_context* ctx, void* dst_device_ptr, size_t bytes);
 /* Adopt a blob that already sits in this device's memory (borrowed: the caller keeps it alive). */
 int rt_adopt_scene_blob(rt_context* ctx, void* device_ptr, size_t bytes);
 
+/* Host-only twin of the packing step of rt_upload_scene: same validation, same blob (see csrc/scene_blob.h), returned
+ * in malloc'ed host memory (free with rt_free_host). Needs no device; err (optional) receives the message on failure. */
+int rt_pack_scene_host(const float* verts, int V, const int32_t* indices, int T, const void* nodes, int N,
+                       const int32_t* tri_indices, int R, const float* normals, int Vn, const int32_t* normal_indices,
+                       const void* materials, int M, const int32_t* tri_to_material, int top_pairs, void** out_blob,
+                       size_t* out_bytes, char* err, int err_len);
+void rt_free_host(void* p);
+
 /* Replaces clEnqueueWriteBuffer(params) in updateCamera() (RayTracer.cpp:671). */
 int rt_set_params(rt_context* ctx, const float params[32]);
 

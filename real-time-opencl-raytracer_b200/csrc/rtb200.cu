@@ -735,3 +735,20 @@ extern "C" int rt_selftest_range(rt_context* ctx, int64_t samples, uint32_t seed
     *out_mismatches = bad;
     return RT_OK;
 }
+
+// Host-only: validate + pack the reference arrays into the blob layout WITHOUT touching a device (the packing is
+// what rt_upload_scene uploads). For tools and the CPU tests of the layout; free the result with rt_free_host.
+extern "C" int rt_pack_scene_host(const float* verts, int V, const int32_t* indices, int T, const void* nodes, int N,
+                                  const int32_t* tri_indices, int R, const float* normals, int Vn, const int32_t* normal_indices,
+                                  const void* materials, int M, const int32_t* tri_to_material, int top_pairs, void** out_blob,
+                                  size_t* out_bytes, char* err, int err_len) {
+    if (!out_blob || !out_bytes) return RT_E_INVALID;
+    SceneInputs in = {verts, V, indices, T, nodes, N, tri_indices, R, normals, Vn, normal_indices, materials, M, tri_to_material};
+    uint8_t* blob = nullptr;
+    uint64_t bytes = 0;
+    if (pack_scene(in, top_pairs, &blob, &bytes, err, err_len)) return RT_E_INVALID;
+    *out_blob = blob;
+    *out_bytes = (size_t)bytes;
+    return RT_OK;
+}
+extern "C" void rt_free_host(void* p) { free(p); }

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "rt_scene_blob", "rt_copy_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_primary", "rt_trace_device",
     "rt_primary_device", "rt_primary_gather_device", "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free",
     "rt_memcpy_to_host", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
-    "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest", "rt_selftest_range",
+    "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest", "rt_selftest_range", "rt_pack_scene_host", "rt_free_host",
 ]
 
 
@@ -68,6 +68,10 @@ def lib():
         L.rt_set_option.argtypes = [vp, C.c_char_p, i32]
         L.rt_scene_info.argtypes = [vp, vp]
         L.rt_selftest.argtypes = [vp, i64, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.rt_pack_scene_host.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, i32, C.POINTER(vp),
+                                         C.POINTER(C.c_size_t), C.c_char_p, i32]
+        L.rt_free_host.argtypes = [vp]
+        L.rt_free_host.restype = None
         L.rt_selftest_range.argtypes = [vp, i64, C.c_uint32, i32, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
@@ -82,6 +86,31 @@ def _ptr(a):
     if isinstance(a, int):
         return a
     return a.data_ptr()
+
+
+def pack_scene_host(mesh, bvh_nodes, tri_indices, top_pairs=2047, shading=True):
+    """Host-only packing (no GPU needed): returns the blob as a uint8 numpy array, or raises RtError."""
+    c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    verts, indices = c(mesh["verts"], np.float32), c(mesh["indices"], np.int32)
+    nodes, tri = c(bvh_nodes, np.float32), c(tri_indices, np.int32)
+    use_shading = shading and len(mesh.get("normals", ())) > 0 and len(mesh.get("materials", ())) > 0
+    if use_shading:
+        normals, nidx = c(mesh["normals"], np.float32), c(mesh["normal_indices"], np.int32)
+        mats, t2m = c(mesh["materials"], np.float32), c(mesh["tri_to_material"], np.int32)
+        Vn, M = normals.shape[0], mats.shape[0]
+    else:
+        normals = nidx = mats = t2m = None
+        Vn = M = 0
+    out, nbytes, err = C.c_void_p(), C.c_size_t(), C.create_string_buffer(256)
+    rc = lib().rt_pack_scene_host(_ptr(verts), verts.shape[0], _ptr(indices), indices.size // 3, _ptr(nodes), nodes.shape[0],
+                                  _ptr(tri), tri.size, _ptr(normals), Vn, _ptr(nidx), _ptr(mats), M, _ptr(t2m), top_pairs,
+                                  C.byref(out), C.byref(nbytes), err, 256)
+    if rc:
+        raise RtError(f"[{rc}] {err.value.decode()}")
+    try:
+        return np.frombuffer((C.c_char * nbytes.value).from_address(out.value), dtype=np.uint8).copy()
+    finally:
+        lib().rt_free_host(out)
 
 
 class Context:
