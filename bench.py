@@ -317,27 +317,70 @@ def main():
         ctx.set_stream(stream.cuda_stream)
     else:
         # N > 1: params from host each step, own bands traced, framebuffer gathered, rank 0 reads the frame back
-        host_frame = (torch.empty((h, w), dtype=torch.int32) if shared_frame else torch.empty((world, rows_per_rank, w), dtype=torch.int32)).pin_memory()
+        # preferred e2e path: the framebuffer is POSIX shared memory that every rank page-locks; each rank's kernel stores
+        # its bands straight into rank 0's HOST memory over its own PCIe link. Fallbacks: peer-mapped device frame + D2H
+        # on rank 0, then NCCL all_gather + D2H.
+        host_frame = None
+        if not args.nccl_gather:
+            try:
+                host_frame = tiling.HostFrame(dist, ctx, rank, h, w)
+            except Exception as exc:  # noqa: BLE001
+                host_frame = None
+                if rank == 0:
+                    print(f"bench: shared-memory host framebuffer unavailable ({exc})", file=sys.stderr)
+            flag = torch.tensor([1 if host_frame else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if not int(flag.item()) and host_frame:
+                host_frame.close()
+                host_frame = None
+        pinned_frame = (torch.empty((h, w), dtype=torch.int32) if shared_frame else torch.empty((world, rows_per_rank, w), dtype=torch.int32)).pin_memory()
         done = torch.zeros(1, device="cuda")
+
+        def e2e_step():
+            ctx.set_params(params)  # host -> device: this frame's 128-byte Params block, on every rank
+            with torch.cuda.stream(stream):
+                if host_frame:
+                    ctx.primary_gather_device(w, h, None, host_frame.device_alias, part=rank, n_parts=world, band_rows=BAND_ROWS)
+                else:
+                    step()
+                    if shared_frame:
+                        dist.all_reduce(done)  # frame-complete signal: every rank's stores have landed on rank 0
+                        if rank == 0:
+                            ctx.memcpy_to_host(pinned_frame, shared_frame, n_pix * 4)
+                    elif rank == 0:
+                        pinned_frame.copy_(d_gather, non_blocking=True)
+            stream.synchronize()
+            if host_frame:
+                dist.barrier()  # every rank's kernel has finished: the frame in rank 0's host memory is complete
+
+        for _ in range(3):
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ctx.set_params(params)
-            with torch.cuda.stream(stream):
-                step()
-                if shared_frame:
-                    dist.all_reduce(done)  # frame-complete signal: every rank's stores have landed on rank 0
-                    if rank == 0:
-                        ctx.memcpy_to_host(host_frame, shared_frame, n_pix * 4)
-                elif rank == 0:
-                    host_frame.copy_(d_gather, non_blocking=True)
-            stream.synchronize()
+            e2e_step()
         barrier()
         t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if host_frame:
+            call = "rt_set_params + rt_primary_gather_device(bands) storing into a shared-memory host framebuffer page-locked by every rank (each GPU's own PCIe link) + barrier"
+            if rank == 0:  # sanity: the host frame equals the device-side gathered frame
+                with torch.cuda.stream(stream):
+                    step()
+                torch.cuda.synchronize()
+            dist.barrier()
+            if rank == 0 and shared_frame:
+                ctx.memcpy_to_host(pinned_frame, shared_frame, n_pix * 4)
+                if not np.array_equal(pinned_frame.numpy(), host_frame.array):
+                    raise SystemExit("bench: host framebuffer differs from the device framebuffer")
+        elif shared_frame:
+            call = "rt_set_params + rt_primary_gather_device(bands, peer-mapped frame on rank 0) + 1-element all_reduce + frame D2H on rank 0"
+        else:
+            call = "rt_set_params + rt_primary_device(bands) + NCCL all_gather + frame D2H on rank 0"
         e2e = {"value": rays_total * args.steps / float(t.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 128 * world,
-               "d2h_bytes_per_step": int(host_frame.numel() * 4), "call": ("rt_set_params + rt_primary_gather_device(bands, peer-mapped frame on rank 0) + 1-element all_reduce + frame D2H on rank 0"
-                        if shared_frame else "rt_set_params + rt_primary_device(bands) + NCCL all_gather + frame D2H on rank 0")}
+               "d2h_bytes_per_step": int(n_pix * 4), "call": call}
+        if host_frame:
+            host_frame.close()
 
     # clocks: the sampling window covers the K timed steps and the e2e loop; if the timed steps were shorter than
     # two sampling periods, extend the window with more (untimed) steps of the same load

@@ -145,6 +145,11 @@ int rt_ipc_open(rt_context* ctx, const unsigned char handle[64], void** out_devi
 int rt_ipc_close(rt_context* ctx, void* device_ptr);
 int rt_ipc_free(rt_context* ctx, void* device_ptr);
 int rt_memcpy_to_host(rt_context* ctx, void* dst_host, const void* src_device, size_t bytes);
+/* Page-lock caller-owned host memory and get the device alias the kernels can store into directly. With a POSIX
+ * shared-memory framebuffer registered by every rank, each GPU writes its bands straight into the consumer's host
+ * memory over its OWN PCIe link (the gather needs neither NVLink nor a device->host copy on rank 0). */
+int rt_host_register(rt_context* ctx, void* host_ptr, size_t bytes, void** out_device_alias);
+int rt_host_unregister(rt_context* ctx, void* host_ptr);
 /* Shadow rays built in-kernel from rays + their closest hits exactly as vR.cl:1314,1407-1441 and
  * traced any-hit. Entries whose hit idx < 0 produce idx = -1, t = RT_T_INIT. d_shadow_rays_out may
  * be NULL. */

@@ -558,6 +558,25 @@ extern "C" int rt_ipc_free(rt_context* ctx, void* device_ptr) {
     CK(ctx, cudaFree(device_ptr));
     return RT_OK;
 }
+// Page-lock caller-owned host memory (e.g. a POSIX shared-memory framebuffer that several ranks map) and return the
+// device alias kernels can store into directly (zero copy over this GPU's own PCIe link).
+extern "C" int rt_host_register(rt_context* ctx, void* host_ptr, size_t bytes, void** out_device_alias) {
+    if (!ctx || !host_ptr || !bytes || !out_device_alias) return RT_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaHostRegister(host_ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    cudaError_t e = cudaHostGetDevicePointer(out_device_alias, host_ptr, 0);
+    if (e != cudaSuccess) {
+        cudaHostUnregister(host_ptr);
+        return set_err(ctx, RT_E_CUDA, "cudaHostGetDevicePointer failed: %s", cudaGetErrorString(e));
+    }
+    return RT_OK;
+}
+extern "C" int rt_host_unregister(rt_context* ctx, void* host_ptr) {
+    if (!ctx || !host_ptr) return RT_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaHostUnregister(host_ptr));
+    return RT_OK;
+}
 extern "C" int rt_memcpy_to_host(rt_context* ctx, void* dst_host, const void* src_device, size_t bytes) {
     if (!ctx || !dst_host || !src_device) return RT_E_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_version", "rt_set_stream", "rt_synchronize", "rt_upload_scene",
     "rt_scene_blob", "rt_copy_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_primary", "rt_trace_device",
     "rt_primary_device", "rt_primary_gather_device", "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free",
-    "rt_memcpy_to_host", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
+    "rt_memcpy_to_host", "rt_host_register", "rt_host_unregister", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
     "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest", "rt_selftest_range", "rt_pack_scene_host", "rt_free_host",
 ]
 
@@ -61,6 +61,8 @@ def lib():
         L.rt_ipc_close.argtypes = [vp, vp]
         L.rt_ipc_free.argtypes = [vp, vp]
         L.rt_memcpy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
+        L.rt_host_register.argtypes = [vp, vp, C.c_size_t, C.POINTER(vp)]
+        L.rt_host_unregister.argtypes = [vp, vp]
         L.rt_diffuse_rays_device.argtypes = [vp, i64, vp, vp, i32, C.c_uint32, vp, vp]
         L.rt_render_frame_device.argtypes = [vp, i32, i32, i32, i32, i32, vp]
         L.rt_get_counters.argtypes = [vp, vp]
@@ -259,6 +261,15 @@ class Context:
 
     def ipc_free(self, ptr):
         self._ck(lib().rt_ipc_free(self._h, ptr))
+
+    def host_register(self, host_ptr, nbytes):
+        """page-lock host memory; returns the device alias kernels may store into"""
+        p = C.c_void_p()
+        self._ck(lib().rt_host_register(self._h, host_ptr, nbytes, C.byref(p)))
+        return p.value
+
+    def host_unregister(self, host_ptr):
+        self._ck(lib().rt_host_unregister(self._h, host_ptr))
 
     def memcpy_to_host(self, dst, src_ptr, nbytes):
         self._ck(lib().rt_memcpy_to_host(self._h, _ptr(dst), src_ptr, nbytes))

@@ -6,6 +6,9 @@ belongs to rank b % world, which balances sky against terrain. Every rank holds 
 The reference has no multi-device code; this is new.
 
 Everything here is backend agnostic: NCCL over NVLink on GPUs, gloo in the CPU tests."""
+import ctypes
+from multiprocessing import shared_memory
+
 import numpy as np
 import torch
 
@@ -91,3 +94,41 @@ def close_shared_frame(dist, ctx, rank, ptr):
         ctx.ipc_free(ptr)
     else:
         ctx.ipc_close(ptr)
+
+
+class HostFrame:
+    """Framebuffer in POSIX shared memory that every rank page-locks and maps into its GPU: each rank's trace kernel
+    stores its bands straight into the consumer's HOST memory over its own PCIe link (rt_host_register). The frame is
+    complete on rank 0 -- without any device->host copy -- once every rank's kernel has finished."""
+
+    def __init__(self, dist, ctx, rank, h, w, dtype=np.int32):
+        self.dist, self.ctx, self.rank = dist, ctx, rank
+        nbytes = int(h) * int(w) * np.dtype(dtype).itemsize
+        box = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            box = [self.shm.name]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=box[0])
+            try:  # only the creator may unlink; keep Python's resource tracker from doing it when a peer exits
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:  # noqa: BLE001
+                pass
+        self.array = np.ndarray((h, w), dtype=dtype, buffer=self.shm.buf)
+        self.host_ptr = ctypes.addressof(ctypes.c_char.from_buffer(self.shm.buf))
+        self.nbytes = nbytes
+        self.device_alias = ctx.host_register(self.host_ptr, nbytes)
+
+    def close(self):
+        self.ctx.host_unregister(self.host_ptr)
+        self.dist.barrier()
+        self.array = None
+        try:
+            self.shm.close()
+        except BufferError:
+            pass
+        if self.rank == 0:
+            self.shm.unlink()
