@@ -47,7 +47,10 @@ struct TraceArgs {
 #ifndef RTB_MINB_LANES
 #define RTB_MINB_LANES 1
 #endif
-static constexpr int kBlockThreads = 128;
+#ifndef RTB_BLOCK_THREADS
+#define RTB_BLOCK_THREADS 128
+#endif
+static constexpr int kBlockThreads = RTB_BLOCK_THREADS;
 static constexpr int kWarpsPerBlock = kBlockThreads / 32;
 
 // ---- ray sources ---------------------------------------------------------------------------------
