@@ -110,3 +110,57 @@ def ref_host(mode, payload, tmpdir):
     subprocess.run([REF_HOST, mode, fin, fout], check=True, stdout=subprocess.DEVNULL)
     with open(fout, "rb") as f:
         return f.read()
+
+
+# ---- the reference's own OpenCL kernel (oracle/_ref/libref_cl.so; needs an OpenCL ICD, i.e. a GPU box) ----------
+REF_CL = os.path.join(_HERE, "_ref", "libref_cl.so")
+_refcl = None
+
+
+class RefCLUnavailable(RuntimeError):
+    pass
+
+
+def refcl(build_options=""):
+    """Load + initialise the reference OpenCL program once per process; raises RefCLUnavailable if it cannot run here."""
+    global _refcl
+    if _refcl is None:
+        if not os.path.exists(REF_CL):
+            raise RefCLUnavailable("oracle/_ref/libref_cl.so not built (needs /root/reference at build time)")
+        L = C.CDLL(REF_CL)
+        L.refcl_last_error.restype = C.c_char_p
+        L.refcl_device_name.restype = C.c_char_p
+        L.refcl_init.argtypes = [C.c_char_p]
+        L.refcl_upload_scene.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.refcl_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        if L.refcl_init(build_options.encode()):
+            raise RefCLUnavailable(L.refcl_last_error().decode(errors="replace"))
+        _refcl = L
+    return _refcl
+
+
+class RefCLScene:
+    """The reference kernel `raytracer_bvh` on the reference-layout arrays, launched as RayTracer.cpp launches it."""
+
+    def __init__(self, mesh, bvh_nodes, tri_indices, build_options=""):
+        self.L = refcl(build_options)
+        c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        v, i = c(mesh["verts"], np.float32), c(mesh["indices"], np.int32)
+        n, t = c(bvh_nodes, np.float32), c(tri_indices, np.int32)
+        nr, ni = c(mesh["normals"], np.float32), c(mesh["normal_indices"], np.int32)
+        m, t2m = c(mesh["materials"], np.float32), c(mesh["tri_to_material"], np.int32)
+        if self.L.refcl_upload_scene(v.ctypes.data, v.shape[0], i.ctypes.data, i.size // 3, n.ctypes.data, n.shape[0], t.ctypes.data,
+                                     t.size, nr.ctypes.data, nr.shape[0], ni.ctypes.data, m.ctypes.data, m.shape[0], t2m.ctypes.data):
+            raise RuntimeError(self.L.refcl_last_error().decode(errors="replace"))
+
+    def device_name(self):
+        return self.L.refcl_device_name().decode()
+
+    def render_frame(self, params, w, h):
+        p = np.ascontiguousarray(params, dtype=np.float32)
+        out = np.empty((h, w), dtype=np.uint32)
+        ms = C.c_double(0)
+        if self.L.refcl_render(p.ctypes.data, w, h, out.ctypes.data, C.byref(ms)):
+            raise RuntimeError(self.L.refcl_last_error().decode(errors="replace"))
+        return out, ms.value
