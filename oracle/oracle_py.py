@@ -130,6 +130,7 @@ def refcl(build_options=""):
         L = C.CDLL(REF_CL)
         L.refcl_last_error.restype = C.c_char_p
         L.refcl_device_name.restype = C.c_char_p
+        L.refcl_build_note.restype = C.c_char_p
         L.refcl_init.argtypes = [C.c_char_p]
         L.refcl_upload_scene.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -156,6 +157,9 @@ class RefCLScene:
 
     def device_name(self):
         return self.L.refcl_device_name().decode()
+
+    def build_note(self):
+        return self.L.refcl_build_note().decode()
 
     def render_frame(self, params, w, h):
         p = np.ascontiguousarray(params, dtype=np.float32)

@@ -103,6 +103,7 @@ static struct {
         mesh_triangle_index_to_material_index, temp, params, out;
     int num_bvh_tris, num_bvh_nodes, out_w, out_h;
     char device_name[256];
+    char build_note[256];
     char error[4096];
 } S;
 
@@ -119,6 +120,7 @@ static int fail(const char* what, cl_int code) {
 
 const char* refcl_last_error(void) { return S.error; }
 const char* refcl_device_name(void) { return S.device_name; }
+const char* refcl_build_note(void) { return S.build_note; }
 long refcl_source_bytes(void) { return (long)(refcl_source_end - refcl_source); }
 
 /* build_options: NULL/"" = exactly the reference (clBuildProgram without options, RayTracer.cpp:2173) */
@@ -162,6 +164,15 @@ int refcl_init(const char* build_options) {
     S.program = cl.CreateProgramWithSource(S.context, 1, &src, &len, &err);
     if (err != CL_SUCCESS) return fail("clCreateProgramWithSource", err);
     err = cl.BuildProgram(S.program, 1, &S.device, (build_options && build_options[0]) ? build_options : NULL, NULL, NULL);
+    if (err != CL_SUCCESS) {
+        /* NVIDIA's compiler rejects `__global __write_only uint *out_data` (volumeRender.cl:1043: "access qualifier can only
+         * be used for pipe and image type"; the author's AMD compiler accepted it). The source stays untouched: the retry only
+         * adds -D__write_only= on the command line (the qualifier occurs nowhere else in the file). */
+        char opts[512];
+        snprintf(opts, sizeof opts, "%s -D__write_only=", (build_options && build_options[0]) ? build_options : "");
+        err = cl.BuildProgram(S.program, 1, &S.device, opts, NULL, NULL);
+        if (err == CL_SUCCESS) snprintf(S.build_note, sizeof S.build_note, "built with the extra option -D__write_only=");
+    }
     if (err != CL_SUCCESS) {
         int k = snprintf(S.error, sizeof S.error, "clBuildProgram failed (%d): ", (int)err);
         cl.GetProgramBuildInfo(S.program, S.device, CL_PROGRAM_BUILD_LOG, sizeof S.error - k - 1, S.error + k, NULL);
