@@ -16,7 +16,7 @@ struct RayIO {  // rt_ray / rt_hit as two / one 16-byte vectors
     float4 d_pad;   // dx dy dz reserved
 };
 
-enum RaySource { SRC_BUFFER = 0, SRC_PRIMARY = 1, SRC_SHADOW = 2 };
+enum RaySource { SRC_BUFFER = 0, SRC_PRIMARY = 1, SRC_SHADOW = 2, SRC_QUEUE = 3 };
 
 struct TraceArgs {
     SceneView scene;
@@ -39,6 +39,11 @@ struct TraceArgs {
     int* idx_frame_out;       // optional (SRC_PRIMARY): 4-byte/pixel hit-index framebuffer; may be a PEER GPU's memory
                               // (store-fused gather over NVLink: the pixel goes straight into the gathered frame)
     unsigned long long* work_counter;  // persistent-warp work queue head (zeroed before launch)
+    // SRC_QUEUE (wavefront bounce stage): rays {o.xyz, bits(pixel)} {d.xyz, -} whose count lives in device memory;
+    // every ray that hits is appended to the shade queue as {o.xyz, bits(pixel)} {d.xyz, t} {bits(idx), -, -, -}
+    const unsigned long long* n_in_ptr;
+    float4* shade_queue;
+    unsigned long long* n_shade;
 };
 
 #ifndef RTB_MINB_BATCH
@@ -235,6 +240,50 @@ __device__ __forceinline__ unsigned int rgb_to_int(float r, float g, float b) {
     return ((unsigned int)b << 16) | ((unsigned int)g << 8) | ((unsigned int)r);
 }
 
+// One path vertex of raytracer_bvh (volumeRender.cl:1306-1403, 1407-1441, 1493-1497): shading of the hit, the shadow
+// ray towards the light and the mirror-reflection ray. Shared by the megakernel and the wavefront kernels.
+struct PathVertex {
+    f3 rez_color;
+    Ray shadow;
+    Ray reflect;
+};
+__device__ __forceinline__ PathVertex shade_path_vertex(const SceneView& s, f3 light_pos, const Ray& r, int hit_idx, float hit_t) {
+    PathVertex pv;
+    const f3 v0 = ld3(__ldg(s.verts + __ldg(s.indices + hit_idx + 0)));
+    const f3 v1 = ld3(__ldg(s.verts + __ldg(s.indices + hit_idx + 1)));
+    const f3 v2 = ld3(__ldg(s.verts + __ldg(s.indices + hit_idx + 2)));
+    const f3 vn0 = ld3(__ldg(s.normals + __ldg(s.normal_indices + hit_idx + 0)));
+    const f3 vn1 = ld3(__ldg(s.normals + __ldg(s.normal_indices + hit_idx + 1)));
+    const f3 vn2 = ld3(__ldg(s.normals + __ldg(s.normal_indices + hit_idx + 2)));
+    f3 vNew;
+    pv.shadow = shadow_ray(light_pos, r, hit_t, vNew);  // vNew = o + d*(t-0.001)
+    const f3 normal = normalize3(normal_at_tri_point(vNew, v0, v1, v2, vn0, vn1, vn2));
+    const f3 l1 = normalize3(sub3(light_pos, vNew));
+    const f3 v = normalize3(sub3(r.ori, vNew));
+    const f3 n = normalize3(normal);
+    const f3 diffuse = ld3(__ldg(s.mat_diffuse + __ldg(s.tri_to_material + hit_idx / 3)));
+    const f3 f0 = scale3(mk3(40.f, 40.f, 40.f), (1 / 255.0f));
+    pv.rez_color = scale3(cook_torrance_ggx(n, l1, v, diffuse, f0, 0.5f), 3.0f);
+    pv.rez_color = add3(pv.rez_color, mul3(mk3(0.3f, 0.3f, 0.3f), diffuse));
+    {  // reflect(i, n) = i - 2.0f * n * dot(n, i)
+        const float d = dot3(normal, r.dir);
+        const f3 refl = sub3(r.dir, scale3(scale3(normal, 2.0f), d));
+        pv.reflect = ray_init(add3(vNew, scale3(refl, 0.001f)), refl);
+    }
+    return pv;
+}
+// volumeRender.cl:1519-1546: average over the path vertices, scale by the mean shadow coefficient, pack
+__device__ __forceinline__ unsigned int resolve_pixel(f3 color, float shadow_coef_sum, int ray_depth) {
+    if (ray_depth >= 1) {
+        color = div3s(color, (float)ray_depth);
+        shadow_coef_sum /= (float)ray_depth;
+        color = scale3(color, shadow_coef_sum);
+    } else {
+        color = mk3(0.f, 0.f, 0.f);
+    }
+    return rgb_to_int(color.x * 255, color.y * 255, color.z * 255);
+}
+
 template <bool SMEM_TOP>
 __device__ __forceinline__ unsigned int render_pixel(const TraceArgs& a, const float4* smem_pairs, int smem_count, unsigned x,
                                                      unsigned y) {
@@ -251,45 +300,19 @@ __device__ __forceinline__ unsigned int render_pixel(const TraceArgs& a, const f
         float shadow_coef = 1.0f;
         if (hit.idx >= 0) {
             ray_depth++;
-            const f3 v0 = ld3(__ldg(s.verts + __ldg(s.indices + hit.idx + 0)));
-            const f3 v1 = ld3(__ldg(s.verts + __ldg(s.indices + hit.idx + 1)));
-            const f3 v2 = ld3(__ldg(s.verts + __ldg(s.indices + hit.idx + 2)));
-            const f3 vn0 = ld3(__ldg(s.normals + __ldg(s.normal_indices + hit.idx + 0)));
-            const f3 vn1 = ld3(__ldg(s.normals + __ldg(s.normal_indices + hit.idx + 1)));
-            const f3 vn2 = ld3(__ldg(s.normals + __ldg(s.normal_indices + hit.idx + 2)));
-            f3 vNew;
-            const Ray sray = shadow_ray(light_pos, r, hit.t, vNew);  // vNew = o + d*(t-0.001)
-            f3 normal = normalize3(normal_at_tri_point(vNew, v0, v1, v2, vn0, vn1, vn2));
-            const f3 l1 = normalize3(sub3(light_pos, vNew));
-            const f3 v = normalize3(sub3(r.ori, vNew));
-            const f3 n = normalize3(normal);
-            const f3 diffuse = ld3(__ldg(s.mat_diffuse + __ldg(s.tri_to_material + hit.idx / 3)));
-            const f3 f0 = scale3(mk3(40.f, 40.f, 40.f), (1 / 255.0f));
-            f3 rez_color = scale3(cook_torrance_ggx(n, l1, v, diffuse, f0, 0.5f), 3.0f);
-            rez_color = add3(rez_color, mul3(mk3(0.3f, 0.3f, 0.3f), diffuse));
+            const PathVertex pv = shade_path_vertex(s, light_pos, r, hit.idx, hit.t);
             {
-                const TraceResult sh = traverse<true, SMEM_TOP>(s, smem_pairs, smem_count, sray, RTB_T_INIT);
+                const TraceResult sh = traverse<true, SMEM_TOP>(s, smem_pairs, smem_count, pv.shadow, RTB_T_INIT);
                 if (sh.idx >= 0 && sh.t > 0.025f) shadow_coef = 0.25f;
             }
-            color = add3(color, rez_color);
+            color = add3(color, pv.rez_color);
             shadow_coef_sum += shadow_coef;
-            {  // reflect(i, n) = i - 2.0f * n * dot(n, i)
-                const float d = dot3(normal, r.dir);
-                const f3 refl = sub3(r.dir, scale3(scale3(normal, 2.0f), d));
-                r = ray_init(add3(vNew, scale3(refl, 0.001f)), refl);
-            }
+            r = pv.reflect;
         } else {
             continue_path = false;
         }
     }
-    if (ray_depth >= 1) {
-        color = div3s(color, (float)ray_depth);
-        shadow_coef_sum /= (float)ray_depth;
-        color = scale3(color, shadow_coef_sum);
-    } else {
-        color = mk3(0.f, 0.f, 0.f);
-    }
-    return rgb_to_int(color.x * 255, color.y * 255, color.z * 255);
+    return resolve_pixel(color, shadow_coef_sum, ray_depth);
 }
 
 template <bool SMEM_TOP>

@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned long long total = (SRC == SRC_PRIMARY) ? (unsigned long long)a.num_batches * 32ull : (unsigned long long)a.n;
+    const unsigned long long total = (SRC == SRC_PRIMARY) ? (unsigned long long)a.num_batches * 32ull
+                                     : (SRC == SRC_QUEUE) ? __ldg(a.n_in_ptr) : (unsigned long long)a.n;
 
     // warp-local slice of the work queue
     unsigned long long q_next = 0, q_end = 0;
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
 
     // lane state
     bool has_ray = false;
+    bool finished = false;  // SRC_QUEUE: this lane's ray ended in the current iteration
     Ray ray;
     RayX rx;
     float tHit = RTB_T_INIT;
@@ -76,6 +78,12 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                     ray.dir = ld3(d);
                     tHit = o.w;
                     out_index = (long long)item;
+                    active = true;
+                } else if (SRC == SRC_QUEUE) {
+                    const float4 o = __ldg(a.rays_in + 2 * item), d = __ldg(a.rays_in + 2 * item + 1);
+                    ray.ori = ld3(o);
+                    ray.dir = ld3(d);
+                    out_index = (long long)__float_as_int(o.w);  // the pixel this path belongs to
                     active = true;
                 } else if (SRC == SRC_PRIMARY) {
                     int x, y;
@@ -144,7 +152,8 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                 if (hit0 && hit1) {
                     if (t0n > t1n) { const int t = c0; c0 = c1; c1 = t; }
                     if (sp >= RTB_STACK) {  // reference: stack overflow returns -1 and drops the hit (vR.cl:914)
-                        a.hits_out[out_index] = make_float4(__int_as_float(-1), tHit, 0.0f, 0.0f);
+                        if (SRC == SRC_QUEUE) { res.idx = -1; finished = true; }
+                        else a.hits_out[out_index] = make_float4(__int_as_float(-1), tHit, 0.0f, 0.0f);
                         has_ray = false;
                     } else {
                         stack[sp++] = c1;
@@ -155,7 +164,8 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                 } else if (hit1) {
                     cur = c1;
                 } else if (sp == 0) {
-                    a.hits_out[out_index] = make_float4(__int_as_float(res.idx), tHit, res.u, res.v);
+                    if (SRC == SRC_QUEUE) finished = true;
+                    else a.hits_out[out_index] = make_float4(__int_as_float(res.idx), tHit, res.u, res.v);
                     has_ray = false;
                 } else {
                     cur = stack[--sp];
@@ -191,9 +201,27 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                 }
             }
             if (done) {
-                a.hits_out[out_index] = make_float4(__int_as_float(res.idx), tHit, res.u, res.v);
+                if (SRC == SRC_QUEUE) finished = true;
+                else a.hits_out[out_index] = make_float4(__int_as_float(res.idx), tHit, res.u, res.v);
                 has_ray = false;
             }
+        }
+        if (SRC == SRC_QUEUE) {  // hand every ray that finished with a hit to the shade stage (one atomicAdd per warp)
+            const bool push = finished && res.idx >= 0;
+            const unsigned pm = __ballot_sync(FULL, push);
+            if (pm) {
+                const int leader = __ffs(pm) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(a.n_shade, (unsigned long long)__popc(pm));
+                base = __shfl_sync(FULL, base, leader);
+                if (push) {
+                    const unsigned long long slot = base + __popc(pm & lt_mask);
+                    a.shade_queue[3 * slot] = make_float4(ray.ori.x, ray.ori.y, ray.ori.z, __int_as_float((int)out_index));
+                    a.shade_queue[3 * slot + 1] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, tHit);
+                    a.shade_queue[3 * slot + 2] = make_float4(__int_as_float(res.idx), 0.f, 0.f, 0.f);
+                }
+            }
+            finished = false;
         }
         __syncwarp();
     }

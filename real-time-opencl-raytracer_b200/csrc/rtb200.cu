@@ -14,6 +14,7 @@
 
 #include "kernels.cuh"
 #include "kernels_lanes.cuh"
+#include "wavefront.cuh"
 #include "scene_blob.h"
 
 using namespace rtb;
@@ -29,6 +30,9 @@ struct rt_context {
     cudaEvent_t chunk_events[16] = {nullptr};
     cudaStream_t out_stream = nullptr;    // device->host copies of rt_trace chunks
     cudaEvent_t out_events[16] = {nullptr};
+    cudaEvent_t wf_events[6] = {nullptr};
+    void* d_wf = nullptr;                 // wavefront scratch: path state + ray queues + counters
+    size_t wf_bytes = 0;
     // scene
     uint8_t* d_blob = nullptr;
     size_t blob_bytes = 0;
@@ -58,6 +62,10 @@ struct rt_context {
                                 // -1 = auto: batch for in-kernel camera/shadow rays (coherent), lanes for ray buffers
     int opt_refill = 16;         // persistent lanes: refill when this many lanes are empty
     int opt_inner_exit = 8;     // persistent lanes: leave the inner phase when fewer lanes than this still descend
+    int opt_frame_mode = 1;     // rt_render_frame*: 1 = wavefront pipeline (wavefront.cuh), 0 = one-thread-per-pixel megakernel
+    int opt_wf_lanes = 1;       // wavefront bounce stages: 1 = persistent-lanes trace + dense shade kernel, 0 = fused batch kernel
+    int opt_wf_late_div = 1;    // wavefront: grids of the later (smaller) stages are divided by this
+    int opt_wf_split = 0;       // wavefront: blocks per SM given to the shadow stream when it overlaps a trace stage (0 = full grids)
     int opt_fast_box = 0;       // 1 = approximate reciprocal/FMA box test for CLOSEST-hit batch kernels (NOT bit-exact; experiment)
     int opt_tile_order = 0;     // primary-ray tile order (see TraceArgs::tile_order)
     int opt_zero_copy = 1;      // rt_primary: store hits directly into pinned host memory when the destination is pinned
@@ -115,6 +123,7 @@ extern "C" int rt_create(int device_ordinal, rt_context** out_ctx) {
     CK(nullptr, cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->chunk_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : ctx->out_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : ctx->wf_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CK(nullptr, cudaMalloc(&ctx->d_counter, 256));
     memset(&ctx->hdr, 0, sizeof ctx->hdr);
     memset(&ctx->view, 0, sizeof ctx->view);
@@ -145,6 +154,9 @@ extern "C" int rt_destroy(rt_context* ctx) {
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->out_events)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->wf_events)
+        if (ev) cudaEventDestroy(ev);
+    cudaFree(ctx->d_wf);
     if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -258,6 +270,10 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     else if (!strcmp(name, "scheduler")) ctx->opt_scheduler = value < 0 ? -1 : (value ? 1 : 0);
     else if (!strcmp(name, "refill")) ctx->opt_refill = value < 1 ? 1 : (value > 32 ? 32 : value);
     else if (!strcmp(name, "inner_exit")) ctx->opt_inner_exit = value < 0 ? 0 : (value > 32 ? 32 : value);
+    else if (!strcmp(name, "frame_mode")) ctx->opt_frame_mode = value ? 1 : 0;
+    else if (!strcmp(name, "wf_lanes")) ctx->opt_wf_lanes = value ? 1 : 0;
+    else if (!strcmp(name, "wf_late_div")) ctx->opt_wf_late_div = value < 1 ? 1 : value;
+    else if (!strcmp(name, "wf_split")) ctx->opt_wf_split = value < 0 ? 0 : value;
     else if (!strcmp(name, "fast_box")) ctx->opt_fast_box = value ? 1 : 0;
     else if (!strcmp(name, "tile_order")) ctx->opt_tile_order = value < 0 ? 0 : value;
     else if (!strcmp(name, "zero_copy")) ctx->opt_zero_copy = value ? 1 : 0;
@@ -684,11 +700,108 @@ extern "C" int rt_diffuse_rays_device(rt_context* ctx, int64_t n, const rt_ray* 
     return RT_OK;
 }
 
+// The frame as a wavefront pipeline (wavefront.cuh). Trace stages run on the context stream, the shadow stage of
+// bounce k on a second stream concurrently with the trace stage of bounce k+1.
+static int render_wavefront(rt_context* ctx, const TraceArgs& ta, uint32_t* d_out) {
+    const size_t npix = (size_t)ta.w * ta.h;
+    const size_t off_color = 256, off_coef = off_color + 16 * npix, off_depth = off_coef + 4 * npix, off_q = off_depth + 4 * npix;
+    const size_t need = off_q + (5 * 32 + 48) * npix;  // 2 reflection + 3 shadow queues (32 B/ray) + 1 shade queue (48 B/hit)
+    int rc = ensure(ctx, &ctx->d_wf, &ctx->wf_bytes, need);
+    if (rc) return rc;
+    uint8_t* base = (uint8_t*)ctx->d_wf;
+    unsigned long long* cnt = (unsigned long long*)base;  // [0..5] work-queue heads, [8..9] reflection counts, [11..13] shadow counts
+    WavefrontArgs a;
+    memset(&a, 0, sizeof a);
+    a.scene = ta.scene;
+    a.params = ta.params;
+    a.w = ta.w; a.h = ta.h; a.tiles_x = ta.tiles_x; a.part = ta.part; a.n_parts = ta.n_parts; a.band_tile_rows = ta.band_tile_rows;
+    a.num_batches = ta.num_batches; a.tile_order = ta.tile_order; a.order_mul = ta.order_mul;
+    a.color = (float4*)(base + off_color);
+    a.coef = (float*)(base + off_coef);
+    a.depth = (int*)(base + off_depth);
+    a.frame_out = d_out;
+    float4* refl[2] = {(float4*)(base + off_q), (float4*)(base + off_q + 32 * npix)};
+    float4* shad[3] = {(float4*)(base + off_q + 64 * npix), (float4*)(base + off_q + 96 * npix), (float4*)(base + off_q + 128 * npix)};
+    float4* shade_q = (float4*)(base + off_q + 160 * npix);
+    int occ_trace = 1, occ_bounce = 1, occ_shadow = 1, occ_lanes = 1;
+    if ((rc = blocks_per_sm(ctx, trace_lanes_kernel<SRC_QUEUE, false>, 0, &occ_lanes))) return rc;
+    if ((rc = blocks_per_sm(ctx, wf_trace_shade_kernel<true>, 0, &occ_trace))) return rc;
+    if ((rc = blocks_per_sm(ctx, wf_trace_shade_kernel<false>, 0, &occ_bounce))) return rc;
+    if ((rc = blocks_per_sm(ctx, wf_shadow_kernel, 0, &occ_shadow))) return rc;
+    const int split = ctx->opt_wf_split;
+    cudaStream_t s_main = ctx->stream, s_shadow = ctx->out_stream;
+    CK(ctx, cudaMemsetAsync(cnt, 0, 128, s_main));
+    for (int b = 0; b < 3; b++) {
+        WavefrontArgs t = a;
+        t.work_counter = cnt + b;
+        t.rays_in = b ? refl[b - 1] : nullptr;
+        t.n_in = b ? cnt + 8 + (b - 1) : nullptr;
+        t.next_out = b < 2 ? refl[b] : nullptr;
+        t.n_next = b < 2 ? cnt + 8 + b : nullptr;
+        t.shadow_out = shad[b];
+        t.n_shadow = cnt + 11 + b;
+        if (b == 0) {
+            long long blocks = (long long)occ_trace * ctx->num_sms;
+            const long long needed = (a.num_batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
+            if (blocks > needed) blocks = needed;
+            if (blocks < 1) blocks = 1;
+            wf_trace_shade_kernel<true><<<(unsigned)blocks, kBlockThreads, 0, s_main>>>(t);
+        } else if (ctx->opt_wf_lanes) {
+            // trace with the persistent-lanes scheduler; rays that hit go to the shade queue, shaded densely afterwards
+            TraceArgs la;
+            memset(&la, 0, sizeof la);
+            la.scene = a.scene;
+            la.rays_in = t.rays_in;
+            la.n_in_ptr = t.n_in;
+            la.shade_queue = shade_q;
+            la.n_shade = cnt + 14 + (b - 1);
+            la.work_counter = t.work_counter;
+            int per_sm = occ_lanes / (b == 2 ? ctx->opt_wf_late_div : 1);
+            if (per_sm < 1) per_sm = 1;
+            trace_lanes_kernel<SRC_QUEUE, false><<<(unsigned)(per_sm * ctx->num_sms), kBlockThreads, 0, s_main>>>(la, ctx->opt_refill, ctx->opt_inner_exit);
+            CK(ctx, cudaGetLastError());
+            wf_shade_kernel<<<(unsigned)(2 * ctx->num_sms), 256, 0, s_main>>>(t, shade_q, cnt + 14 + (b - 1));
+            ctx->counters[RT_CNT_KERNEL_LAUNCHES] += 1;
+        } else {
+            int per_sm = occ_bounce - (split > 0 && split < occ_bounce ? split : 0);
+            wf_trace_shade_kernel<false><<<(unsigned)(per_sm * ctx->num_sms), kBlockThreads, 0, s_main>>>(t);
+        }
+        CK(ctx, cudaGetLastError());
+        CK(ctx, cudaEventRecord(ctx->wf_events[b], s_main));
+        CK(ctx, cudaStreamWaitEvent(s_shadow, ctx->wf_events[b], 0));
+        WavefrontArgs sh = a;
+        sh.work_counter = cnt + 3 + b;
+        sh.rays_in = shad[b];
+        sh.n_in = cnt + 11 + b;
+        int sh_per_sm = (split > 0 && split < occ_shadow && b < 2) ? split : occ_shadow;
+        if (b > 0) sh_per_sm = sh_per_sm / ctx->opt_wf_late_div > 0 ? sh_per_sm / ctx->opt_wf_late_div : 1;
+        wf_shadow_kernel<<<(unsigned)(sh_per_sm * ctx->num_sms), kBlockThreads, 0, s_shadow>>>(sh);
+        CK(ctx, cudaGetLastError());
+        ctx->counters[RT_CNT_KERNEL_LAUNCHES] += 2;
+    }
+    CK(ctx, cudaEventRecord(ctx->wf_events[3], s_shadow));
+    CK(ctx, cudaStreamWaitEvent(s_main, ctx->wf_events[3], 0));
+    const long long threads = a.num_batches * 32;
+    wf_resolve_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s_main>>>(a);
+    CK(ctx, cudaGetLastError());
+    ctx->counters[RT_CNT_KERNEL_LAUNCHES] += 1;
+    return RT_OK;
+}
+
 extern "C" int rt_render_frame_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, uint32_t* d_out) {
     int rc = require(ctx, true, true);
     if (rc) return rc;
     if (!d_out) return set_err(ctx, RT_E_INVALID, "rt_render_frame_device: d_out is NULL");
     CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->opt_frame_mode == 1 && smem_top_count(ctx) == 0) {
+        TraceArgs ta;
+        memset(&ta, 0, sizeof ta);
+        ta.scene = ctx->view;
+        ta.params = ctx->params;
+        if ((rc = band_setup(ctx, ta, w, h, part, n_parts, band_rows))) return rc;
+        if (ta.num_batches < 1) return RT_OK;
+        return render_wavefront(ctx, ta, d_out);
+    }
     TraceArgs a;
     memset(&a, 0, sizeof a);
     a.scene = ctx->view;

@@ -71,8 +71,8 @@ __device__ __forceinline__ TraceResult traverse(const SceneView& s, const float4
             }
             float t0n, t0f, t1n, t1f;
             if (FAST_BOX) {
-                ray_box_fast(rf, q0, q1, t0n, t0f);
-                ray_box_fast(rf, q2, q3, t1n, t1f);
+                ray_box_fast(ray, rf, q0, q1, t0n, t0f);
+                ray_box_fast(ray, rf, q2, q3, t1n, t1f);
             } else if (rx.fast) {
                 ray_box_hoisted(rx, q0, q1, t0n, t0f);
                 ray_box_hoisted(rx, q2, q3, t1n, t1f);

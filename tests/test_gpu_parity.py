@@ -177,6 +177,35 @@ def test_medium_scene_all_ray_classes_vs_oracle(ctx):
     assert d.max() <= 1 and (d.max(axis=-1) > 0).mean() < 0.02
 
 
+@pytest.mark.parametrize("name", ["mix", "terrain12", "ico2"])
+def test_wavefront_frame_equals_megakernel(ctx, name):
+    """rt_render_frame: the wavefront pipeline (default) and the one-thread-per-pixel megakernel give the same pixels, bit for
+    bit, with either scheduler for the bounce stages"""
+    import torch
+
+    g = load_scene(name)
+    _upload(ctx, g)
+    w, h = 160, 100
+    params, _ = rtb200.camera_params(w, h, g["aabb_min"], g["aabb_max"], light_pos=(-150.0, 25.0, 3.0))
+    ctx.set_params(params)
+    frames = []
+    try:
+        for mode, lanes in ((0, 0), (1, 0), (1, 1)):
+            ctx.set_option("frame_mode", mode)
+            ctx.set_option("wf_lanes", lanes)
+            img = torch.full((h, w), -1, dtype=torch.int32, device="cuda")
+            ctx.render_frame_device(w, h, img)
+            ctx.render_frame_device(w, h, img)  # a second frame re-uses the queues
+            ctx.synchronize()
+            frames.append(img.cpu())
+    finally:
+        ctx.set_option("frame_mode", 1)
+        ctx.set_option("wf_lanes", 1)
+    assert torch.equal(frames[0], frames[1]) and torch.equal(frames[0], frames[2])
+    ref_img, _ = O.OracleScene(mesh_dict(g), g["ref_nodes"], g["ref_tri_indices"]).render_frame(params, w, h)
+    assert channel_diff(frames[2].numpy().view(np.uint32), ref_img).max() <= 1
+
+
 def test_band_partition_covers_frame(ctx):
     """interleaved row bands (the multi-GPU partition) of the fused primary + frame kernels tile the frame exactly"""
     import torch
