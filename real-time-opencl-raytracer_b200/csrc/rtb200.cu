@@ -704,8 +704,9 @@ extern "C" int rt_diffuse_rays_device(rt_context* ctx, int64_t n, const rt_ray* 
 // bounce k on a second stream concurrently with the trace stage of bounce k+1.
 static int render_wavefront(rt_context* ctx, const TraceArgs& ta, uint32_t* d_out) {
     const size_t npix = (size_t)ta.w * ta.h;
-    const size_t off_color = 256, off_coef = off_color + 16 * npix, off_depth = off_coef + 4 * npix, off_q = off_depth + 4 * npix;
-    const size_t need = off_q + (5 * 32 + 48) * npix;  // 2 reflection + 3 shadow queues (32 B/ray) + 1 shade queue (48 B/hit)
+    const size_t npad = (npix + 63) & ~(size_t)63;  // every section stays 256-byte aligned (float4 queues)
+    const size_t off_color = 256, off_coef = off_color + 16 * npad, off_depth = off_coef + 4 * npad, off_q = off_depth + 4 * npad;
+    const size_t need = off_q + (5 * 32 + 48) * npad;  // 2 reflection + 3 shadow queues (32 B/ray) + 1 shade queue (48 B/hit)
     int rc = ensure(ctx, &ctx->d_wf, &ctx->wf_bytes, need);
     if (rc) return rc;
     uint8_t* base = (uint8_t*)ctx->d_wf;
@@ -720,9 +721,9 @@ static int render_wavefront(rt_context* ctx, const TraceArgs& ta, uint32_t* d_ou
     a.coef = (float*)(base + off_coef);
     a.depth = (int*)(base + off_depth);
     a.frame_out = d_out;
-    float4* refl[2] = {(float4*)(base + off_q), (float4*)(base + off_q + 32 * npix)};
-    float4* shad[3] = {(float4*)(base + off_q + 64 * npix), (float4*)(base + off_q + 96 * npix), (float4*)(base + off_q + 128 * npix)};
-    float4* shade_q = (float4*)(base + off_q + 160 * npix);
+    float4* refl[2] = {(float4*)(base + off_q), (float4*)(base + off_q + 32 * npad)};
+    float4* shad[3] = {(float4*)(base + off_q + 64 * npad), (float4*)(base + off_q + 96 * npad), (float4*)(base + off_q + 128 * npad)};
+    float4* shade_q = (float4*)(base + off_q + 160 * npad);
     int occ_trace = 1, occ_bounce = 1, occ_shadow = 1, occ_lanes = 1;
     if ((rc = blocks_per_sm(ctx, trace_lanes_kernel<SRC_QUEUE, false>, 0, &occ_lanes))) return rc;
     if ((rc = blocks_per_sm(ctx, wf_trace_shade_kernel<true>, 0, &occ_trace))) return rc;
