@@ -119,6 +119,21 @@ def oracle_pass(arrays, bvh, params, w, h, repeats, threads=None):
     return times, cnt, live.shape[0], O.lib().orc_num_threads()
 
 
+def reference_opencl_frame(arrays, bvh, params, w, h, repeats=5):
+    """The reference's OWN OpenCL kernel (unmodified, oracle/_ref/libref_cl.so) on this box's OpenCL device -- on the GPU
+    boxes that is the same B200 through NVIDIA's ICD. It renders the whole frame (primary + shadow + reflections + shading):
+    returns the median kernel time, or None where no OpenCL device / no prebuilt library exists."""
+    try:
+        from oracle import oracle_py as O
+
+        ref = O.RefCLScene(arrays, bvh.nodes, bvh.tri_indices)
+        ms = [ref.render_frame(params, w, h)[1] for _ in range(repeats + 1)][1:]
+        return {"device": ref.device_name(), "kernel": "raytracer_bvh (volumeRender.cl, unmodified)", "frame": [w, h],
+                "frame_kernel_ms": float(np.median(ms)), "build_note": ref.build_note()}
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": str(exc)[:200]}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path. pocl/OpenCL do not exist in
     this image, so this is the oracle port (oracle/oracle.c, line-by-line restatement of volumeRender.cl)
@@ -146,6 +161,7 @@ def run_reference(args):
                          "sample": f"the full {w}x{h} frame ({nrays} traversed rays) per step, {len(timed)} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_opencl": reference_opencl_frame(arrays, bvh, params, w, h),
     }
     print(json.dumps(line))
 
@@ -431,6 +447,22 @@ def main():
             line["roofline"] = roof
         if cpu:
             line["cpu_baseline"] = cpu
+        if world == 1:
+            # same-hardware comparison on the reference's own unit of work (one shaded frame): its kernel vs rt_render_frame
+            ref_cl = reference_opencl_frame(arrays, bvh, params, w, h)
+            d_img = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+            ts = []
+            for i in range(8):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e0.record()
+                    ctx.render_frame_device(w, h, d_img)
+                    e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ts.append(e0.elapsed_time(e1))
+            ref_cl["ours_frame_kernel_ms"] = float(np.median(ts))
+            line["reference_opencl"] = ref_cl
         if args.extra and world == 1:
             line["extra"] = extra_passes(ctx, torch, rtb200, w, h, stream)
         print(json.dumps(line))
