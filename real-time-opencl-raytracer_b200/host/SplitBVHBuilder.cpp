@@ -265,29 +265,30 @@ SplitBVHBuilder::SpatialSplit SplitBVHBuilder::findSpatialSplit(Task& t, const N
     }
 
     // Pick the cheapest of the 127 planes per axis.
-    SpatialSplit split;
+    SpatialSplit best;
     for (int dim = 0; dim < 3; dim++) {
-        AABB rightBox;
-        for (int i = NumSpatialBins - 1; i > 0; i--) {
-            rightBox.grow(bin(dim, i).bounds);
-            t.rightBounds[i - 1] = rightBox;
+        AABB suffix;  // bounds of bins [plane, NumSpatialBins), built back to front
+        for (int plane = NumSpatialBins - 1; plane >= 1; plane--) {
+            suffix.grow(bin(dim, plane).bounds);
+            t.rightBounds[plane - 1] = suffix;
         }
-        AABB leftBox;
-        int leftNum = 0, rightNum = spec.numRef;
-        for (int i = 1; i < NumSpatialBins; i++) {
-            leftBox.grow(bin(dim, i - 1).bounds);
-            leftNum += bin(dim, i - 1).enter;
-            rightNum -= bin(dim, i - 1).exit;
-            const F32 sah = nodeSAH + leftBox.area() * m_platform.getTriangleCost(leftNum) +
-                            t.rightBounds[i - 1].area() * m_platform.getTriangleCost(rightNum);
-            if (sah < split.sah) {
-                split.sah = sah;
-                split.dim = dim;
-                split.pos = origin.m[dim] + binSize.m[dim] * (F32)i;
+        AABB prefix;  // bounds of bins [0, plane)
+        int startedLeft = 0, notYetEnded = spec.numRef;
+        for (int plane = 1; plane < NumSpatialBins; plane++) {
+            const SpatialBin& passed = bin(dim, plane - 1);
+            prefix.grow(passed.bounds);
+            startedLeft += passed.enter;
+            notYetEnded -= passed.exit;
+            const F32 sah = nodeSAH + prefix.area() * m_platform.getTriangleCost(startedLeft) +
+                            t.rightBounds[plane - 1].area() * m_platform.getTriangleCost(notYetEnded);
+            if (sah < best.sah) {
+                best.sah = sah;
+                best.dim = dim;
+                best.pos = origin.m[dim] + binSize.m[dim] * (F32)plane;
             }
         }
     }
-    return split;
+    return best;
 }
 
 // In-place three-way partition of the node's range into [left | straddling | right], then each
@@ -301,51 +302,59 @@ void SplitBVHBuilder::performSpatialSplit(Task& t, NodeSpec& left, NodeSpec& rig
     left.bounds = right.bounds = AABB();
     t.sortedDim = -1;
 
-    for (int i = leftEnd; i < rightStart; i++) {
-        if (refs[i].bounds.maxf().m[split.dim] <= split.pos) {  // entirely left
-            left.bounds.grow(refs[i].bounds);
-            swap1(refs[i], refs[leftEnd++]);
-        } else if (refs[i].bounds.minf().m[split.dim] >= split.pos) {  // entirely right
-            right.bounds.grow(refs[i].bounds);
-            swap1(refs[i], refs[--rightStart]);
-            i--;  // re-examine what was swapped in
+    const int axis = split.dim;
+    for (int scan = leftEnd; scan < rightStart;) {
+        const AABB& b = refs[scan].bounds;
+        if (b.maxf().m[axis] <= split.pos) {  // wholly left of the plane: move to the growing left block
+            left.bounds.grow(b);
+            swap1(refs[scan], refs[leftEnd]);
+            ++leftEnd;
+            ++scan;
+        } else if (b.minf().m[axis] >= split.pos) {  // wholly right: swap with the last unclassified one, look at it next
+            right.bounds.grow(b);
+            --rightStart;
+            swap1(refs[scan], refs[rightStart]);
+        } else {
+            ++scan;  // straddles the plane: decided below
         }
     }
 
+    // Straddlers sit in [leftEnd, rightStart). For each, three candidates are costed with the surface-area heuristic:
+    // keep it whole on the left, keep it whole on the right, or clip it and reference it from both sides.
     while (leftEnd < rightStart) {
-        Reference lref, rref;
-        splitReference(lref, rref, refs[leftEnd], split.dim, split.pos);
+        const Reference& straddler = refs[leftEnd];
+        Reference clippedL, clippedR;
+        splitReference(clippedL, clippedR, straddler, split.dim, split.pos);
 
-        AABB lub = left.bounds;   // unsplit to the left
-        AABB rub = right.bounds;  // unsplit to the right
-        AABB ldb = left.bounds;   // duplicate, left half
-        AABB rdb = right.bounds;  // duplicate, right half
-        lub.grow(refs[leftEnd].bounds);
-        rub.grow(refs[leftEnd].bounds);
-        ldb.grow(lref.bounds);
-        rdb.grow(rref.bounds);
+        AABB leftIfWhole = left.bounds, rightIfWhole = right.bounds;  // bounds if the whole reference joins that side
+        AABB leftIfClipped = left.bounds, rightIfClipped = right.bounds;
+        leftIfWhole.grow(straddler.bounds);
+        rightIfWhole.grow(straddler.bounds);
+        leftIfClipped.grow(clippedL.bounds);
+        rightIfClipped.grow(clippedR.bounds);
 
-        const F32 lac = m_platform.getTriangleCost(leftEnd - leftStart);
-        const F32 rac = m_platform.getTriangleCost((int)refs.size() - rightStart);
-        const F32 lbc = m_platform.getTriangleCost(leftEnd - leftStart + 1);
-        const F32 rbc = m_platform.getTriangleCost((int)refs.size() - rightStart + 1);
+        const int nLeft = leftEnd - leftStart, nRight = (int)refs.size() - rightStart;
+        const F32 costLeftNow = m_platform.getTriangleCost(nLeft), costRightNow = m_platform.getTriangleCost(nRight);
+        const F32 costLeftPlus = m_platform.getTriangleCost(nLeft + 1), costRightPlus = m_platform.getTriangleCost(nRight + 1);
 
-        const F32 unsplitLeftSAH = lub.area() * lbc + right.bounds.area() * rac;
-        const F32 unsplitRightSAH = left.bounds.area() * lac + rub.area() * rbc;
-        const F32 duplicateSAH = ldb.area() * lbc + rdb.area() * rbc;
-        const F32 minSAH = fminf1(unsplitLeftSAH, unsplitRightSAH, duplicateSAH);
+        const F32 sahWholeLeft = leftIfWhole.area() * costLeftPlus + right.bounds.area() * costRightNow;
+        const F32 sahWholeRight = left.bounds.area() * costLeftNow + rightIfWhole.area() * costRightPlus;
+        const F32 sahBoth = leftIfClipped.area() * costLeftPlus + rightIfClipped.area() * costRightPlus;
+        const F32 best = fminf1(sahWholeLeft, sahWholeRight, sahBoth);
 
-        if (minSAH == unsplitLeftSAH) {
-            left.bounds = lub;
-            leftEnd++;
-        } else if (minSAH == unsplitRightSAH) {
-            right.bounds = rub;
-            std::swap(refs[leftEnd], refs[--rightStart]);
+        if (best == sahWholeLeft) {  // checked in this order: whole-left wins ties, then whole-right
+            left.bounds = leftIfWhole;
+            ++leftEnd;
+        } else if (best == sahWholeRight) {
+            right.bounds = rightIfWhole;
+            --rightStart;
+            std::swap(refs[leftEnd], refs[rightStart]);
         } else {
-            left.bounds = ldb;
-            right.bounds = rdb;
-            refs[leftEnd++] = lref;
-            refs.push_back(rref);
+            left.bounds = leftIfClipped;
+            right.bounds = rightIfClipped;
+            refs[leftEnd] = clippedL;
+            ++leftEnd;
+            refs.push_back(clippedR);  // appended references belong to the right side
         }
     }
     left.numRef = leftEnd - leftStart;
@@ -359,21 +368,23 @@ void SplitBVHBuilder::splitReference(Reference& left, Reference& right, const Re
     left.triIdx = right.triIdx = ref.triIdx;
     left.bounds = right.bounds = AABB();
 
-    const int3& inds = m_tris[ref.triIdx];
-    const float4* v1 = &m_verts[inds.z];
-    for (int i = 0; i < 3; i++) {
-        const float4* v0 = v1;
-        v1 = &m_verts[inds.m[i]];
-        const F32 v0p = v0->get(dim);
-        const F32 v1p = v1->get(dim);
-
-        if (v0p <= pos) left.bounds.grow(make_float3(v0->x, v0->y, v0->z));
-        if (v0p >= pos) right.bounds.grow(make_float3(v0->x, v0->y, v0->z));
-
-        if ((v0p < pos && v1p > pos) || (v0p > pos && v1p < pos)) {
-            const float4 p = lerp(*v0, *v1, clamp((pos - v0p) / (v1p - v0p), 0.0f, 1.0f));
-            left.bounds.grow(make_float3(p.x, p.y, p.z));
-            right.bounds.grow(make_float3(p.x, p.y, p.z));
+    const int3& corner = m_tris[ref.triIdx];
+    // edges (c -> a), (a -> b), (b -> c): each start vertex is sorted into the side(s) it lies on, each edge that
+    // crosses the plane contributes its intersection point to both sides
+    const int order[4] = {corner.z, corner.x, corner.y, corner.z};
+    for (int e = 0; e < 3; e++) {
+        const float4& from = m_verts[order[e]];
+        const float4& to = m_verts[order[e + 1]];
+        const F32 fromP = from.get(dim), toP = to.get(dim);
+        const float3 fromPoint = make_float3(from.x, from.y, from.z);
+        if (fromP <= pos) left.bounds.grow(fromPoint);
+        if (fromP >= pos) right.bounds.grow(fromPoint);
+        const bool crosses = (fromP < pos && toP > pos) || (fromP > pos && toP < pos);
+        if (crosses) {
+            const float4 hit = lerp(from, to, clamp((pos - fromP) / (toP - fromP), 0.0f, 1.0f));
+            const float3 hitPoint = make_float3(hit.x, hit.y, hit.z);
+            left.bounds.grow(hitPoint);
+            right.bounds.grow(hitPoint);
         }
     }
     left.bounds.maxf().m[dim] = pos;
