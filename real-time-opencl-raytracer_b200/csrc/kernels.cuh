@@ -60,6 +60,28 @@ static constexpr int kWarpsPerBlock = kBlockThreads / 32;
 
 // ---- ray sources ---------------------------------------------------------------------------------
 
+// Cheap, conservative pre-test of the scene-AABB gate: true only if the pixel's ray CERTAINLY fails the exact gate
+// below, so that the exact ray (2 IEEE divisions, normalise, 3 more divisions) need not be built for it. Most pixels of
+// a typical frame look past the scene; they cost ~25 instead of ~150 instructions. The slab test is invariant under
+// positive scaling of the direction, so the unnormalised direction and approximate reciprocals (error ~1e-6) are
+// enough; decisions within a 1e-3 relative margin, and anything non-finite, are left to the exact path.
+__device__ __forceinline__ bool certainly_gated_out(const ParamsBlock& P, unsigned x, unsigned y, unsigned w, unsigned h) {
+    const float xf = ((float)x - 0.5f) * rcp_approx((float)w), yf = ((float)y - 0.5f) * rcp_approx((float)h);
+    const float ox = __fmaf_rn(P.b.x, yf, __fmaf_rn(P.a.x, xf, P.c.x));
+    const float oy = __fmaf_rn(P.b.y, yf, __fmaf_rn(P.a.y, xf, P.c.y));
+    const float oz = __fmaf_rn(P.b.z, yf, __fmaf_rn(P.a.z, xf, P.c.z));
+    const float ix = rcp_approx(ox - P.campos.x), iy = rcp_approx(oy - P.campos.y), iz = rcp_approx(oz - P.campos.z);
+    const float ax = (P.aabb_min.x - ox) * ix, bx = (P.aabb_max.x - ox) * ix;
+    const float ay = (P.aabb_min.y - oy) * iy, by = (P.aabb_max.y - oy) * iy;
+    const float az = (P.aabb_min.z - oz) * iz, bz = (P.aabb_max.z - oz) * iz;
+    const float mag = fmaxf(fmaxf(fmaxf(fabsf(ax), fabsf(bx)), fmaxf(fabsf(ay), fabsf(by))), fmaxf(fabsf(az), fabsf(bz)));
+    if (!(mag < 1e30f)) return false;  // inf / NaN somewhere (axis-parallel ray, degenerate box): decide exactly
+    const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    const float margin = 1e-3f * mag;
+    return (tmax < tmin - margin) || (tmax < -margin);
+}
+
 // volumeRender.cl:1156-1196: pixel -> primary ray; returns the scene-AABB gate
 __device__ __forceinline__ bool primary_ray(const ParamsBlock& P, unsigned x, unsigned y, unsigned w, unsigned h, Ray& r) {
     // (x-0.5)/((float)w): exact in fp32 (see oracle/oracle.c primary_ray)
@@ -137,7 +159,8 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
             tile_pixel(a, (long long)batch, lane, x, y);
             if (x < a.w && y < a.h) {
                 out_index = (long long)y * a.w + x;
-                active = primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray);
+                if (a.rays_out || !certainly_gated_out(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h))
+                    active = primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray);
                 if (a.rays_out) store_ray(a.rays_out, out_index, ray);
                 if (!active) {
                     if (a.hits_out) a.hits_out[out_index] = make_float4(__int_as_float(-1), RTB_T_INIT, 0.0f, 0.0f);
@@ -290,7 +313,8 @@ __device__ __forceinline__ unsigned int render_pixel(const TraceArgs& a, const f
     const SceneView& s = a.scene;
     const f3 light_pos = ld3(a.params.light_pos);
     Ray r;
-    bool continue_path = primary_ray(a.params, x, y, (unsigned)a.w, (unsigned)a.h, r);
+    bool continue_path = !certainly_gated_out(a.params, x, y, (unsigned)a.w, (unsigned)a.h) &&
+                         primary_ray(a.params, x, y, (unsigned)a.w, (unsigned)a.h, r);
     f3 color = mk3(0.f, 0.f, 0.f);
     int ray_depth = 0;
     float shadow_coef_sum = 0.0f;

@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                     tile_pixel(a, (long long)(item >> 5), (int)(item & 31), x, y);
                     if (x < a.w && y < a.h) {
                         out_index = (long long)y * a.w + x;
-                        active = primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray);
+                        if (a.rays_out || !certainly_gated_out(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h))
+                            active = primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray);
                         if (a.rays_out) store_ray(a.rays_out, out_index, ray);
                         if (!active) a.hits_out[out_index] = make_float4(__int_as_float(-1), RTB_T_INIT, 0.0f, 0.0f);
                     }

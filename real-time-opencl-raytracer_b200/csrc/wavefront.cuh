@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(kBlockThreads) wf_trace_shade_kernel(const Wav
             tile_pixel(t, (long long)batch, lane, x, y);
             if (x < a.w && y < a.h) {
                 pixel = y * a.w + x;
-                active = primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray);
+                active = !certainly_gated_out(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h) &&
+                         primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray);
                 a.color[pixel] = make_float4(0.f, 0.f, 0.f, 0.f);
                 a.coef[pixel] = 0.0f;
                 a.depth[pixel] = 0;

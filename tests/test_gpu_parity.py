@@ -206,6 +206,32 @@ def test_wavefront_frame_equals_megakernel(ctx, name):
     assert channel_diff(frames[2].numpy().view(np.uint32), ref_img).max() <= 1
 
 
+def test_gate_pretest_never_drops_a_hit(ctx):
+    """the conservative approximate scene-gate pre-test only skips pixels the exact gate rejects anyway: primary hits
+    stay bit-identical to the oracle from far, near, inside-the-box, grazing and axis-parallel camera poses"""
+    import torch
+
+    g = load_scene("mix")
+    _upload(ctx, g)
+    sc = O.OracleScene(mesh_dict(g), g["ref_nodes"], g["ref_tri_indices"])
+    w, h = 128, 96
+    poses = [dict(), dict(d_radius=1500.0), dict(d_radius=-150.0), dict(d_radius=-195.0), dict(d_beta=-0.78), dict(d_beta=0.7),
+             dict(d_alpha=0.7853982, d_beta=-0.7853982)]
+    for pose in poses:
+        params, _ = rtb200.camera_params(w, h, g["aabb_min"], g["aabb_max"], **pose)
+        ctx.set_params(params)
+        rays, gate = O.primary_rays(params, w, h)
+        want, _ = sc.trace(0, rays)
+        want[gate == 0] = (-1, rtb200.T_INIT, 0, 0)
+        d_hits = torch.zeros((w * h, 4), device="cuda")
+        ctx.primary_device(w, h, d_hits)
+        ctx.synchronize()
+        assert_hits_identical(d_hits.cpu().numpy().view(HIT).reshape(-1), want, f"pose {pose}")
+        img = ctx.render_frame(w, h)
+        ref_img, _ = sc.render_frame(params, w, h)
+        assert channel_diff(img, ref_img).max() <= 1, pose
+
+
 def test_band_partition_covers_frame(ctx):
     """interleaved row bands (the multi-GPU partition) of the fused primary + frame kernels tile the frame exactly"""
     import torch
