@@ -80,9 +80,14 @@ def open_shared_frame(dist, ctx, rank, nbytes):
     box = [None]
     ptr = None
     if rank == 0:
-        ptr, handle = ctx.ipc_alloc(nbytes)
-        box = [handle]
+        try:
+            ptr, handle = ctx.ipc_alloc(nbytes)
+            box = [handle]
+        except Exception as exc:  # noqa: BLE001  -- tell the peers instead of leaving them in the broadcast
+            box = [exc]
     dist.broadcast_object_list(box, src=0)
+    if isinstance(box[0], Exception):
+        raise RuntimeError(f"rank 0 could not create the shared framebuffer: {box[0]}")
     if rank != 0:
         ptr = ctx.ipc_open(box[0])
     return ptr
@@ -106,9 +111,14 @@ class HostFrame:
         nbytes = int(h) * int(w) * np.dtype(dtype).itemsize
         box = [None]
         if rank == 0:
-            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
-            box = [self.shm.name]
+            try:
+                self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+                box = [self.shm.name]
+            except Exception as exc:  # noqa: BLE001  (e.g. /dev/shm too small) -- tell the peers
+                box = [exc]
         dist.broadcast_object_list(box, src=0)
+        if isinstance(box[0], Exception):
+            raise RuntimeError(f"rank 0 could not create the shared-memory framebuffer: {box[0]}")
         if rank != 0:
             self.shm = shared_memory.SharedMemory(name=box[0])
             try:  # only the creator may unlink; keep Python's resource tracker from doing it when a peer exits
