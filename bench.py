@@ -227,6 +227,7 @@ def main():
         bcast_ms = e0.elapsed_time(e1)
         params = pt.cpu().numpy()
     ctx.set_params(params)
+    ctx_params[0] = params
 
     # ---- buffers ---------------------------------------------------------------------------------
     d_hits = torch.zeros((n_pix, 4), dtype=torch.float32, device="cuda")
@@ -438,7 +439,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{w}x{h} primary rays ({rays_total} traversed/step) vs 999698-triangle displaced-grid terrain, SBVH via SplitBVHBuilder "
                                    f"(BASELINE configs[1]{'' if world == 1 else '; frame scaled with N at 16:9, interleaved 16-row bands, NCCL scene broadcast + framebuffer all_gather'})",
-                       "frame": [w, h], "rays_per_step": rays_total, "l2": "not flushed" if args.no_flush else "flushed between timed steps (256 MiB fill)",
+                       "frame": [w, h], "rays_per_step": rays_total, "pixels_per_step": n_pix,
+                       "mpixels_per_s": n_pix * args.steps / (total_ms * 1e-3) / 1e6, "l2": "not flushed" if args.no_flush else "flushed between timed steps (256 MiB fill)",
                        "scene_build_s": build_s, "scene_broadcast_ms": bcast_ms, "band_rows": BAND_ROWS,
                        "gather": "n/a (1 GPU)" if world == 1 else ("fused into the kernel store: peer-mapped framebuffer on rank 0 over NVLink (CUDA IPC)" if shared_frame else "NCCL all_gather of 4-byte/pixel bands")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
@@ -499,6 +501,9 @@ def load_traffic():
         return None
 
 
+ctx_params = [None]
+
+
 def extra_passes(ctx, torch, rtb200, w, h, stream):
     """shadow / diffuse / frame throughput on the same scene (informational; not the headline metric)."""
     n = w * h
@@ -539,6 +544,15 @@ def extra_passes(ctx, torch, rtb200, w, h, stream):
     d_img = torch.zeros((h, w), dtype=torch.int32, device="cuda")
     ms = timed(lambda: ctx.render_frame_device(w, h, d_img), iters=5)
     out["full_frame_ms"] = ms
+    ctx.set_option("frame_mode", 0)
+    out["full_frame_megakernel_ms"] = timed(lambda: ctx.render_frame_device(w, h, d_img), iters=5)
+    ctx.set_option("frame_mode", 1)
+    # NOT the shipped default: closest-hit traversal with the reciprocal-multiply box test (not bit-exact)
+    ctx.set_option("fast_box", 1)
+    ms = timed(lambda: ctx.primary_device(w, h, d_hits))
+    ctx.set_option("fast_box", 0)
+    ntrav = count_gate_pass(ctx_params[0], w, h, list(range(h)))
+    out["primary_mrays_s_with_inexact_fast_box_option"] = ntrav / ms / 1e3
     return out
 
 
