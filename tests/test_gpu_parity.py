@@ -232,6 +232,51 @@ def test_gate_pretest_never_drops_a_hit(ctx):
         assert channel_diff(img, ref_img).max() <= 1, pose
 
 
+@pytest.mark.parametrize("seed,scale", [(1, 1.0), (2, 1e-2), (3, 1e3), (4, 37.0), (5, 0.3)])
+def test_random_triangle_soup_fuzz(ctx, seed, scale):
+    """random soups with degenerate (zero-area, repeated-vertex), axis-aligned and overlapping triangles at several scales,
+    rays that start inside boxes, run along axes (zero direction components, signed zeros) or carry finite tmax:
+    closest and any-hit stay bit-identical to the oracle (NaN/inf behaviour of the slab and Moller-Trumbore tests included)"""
+    rng = np.random.default_rng(seed)
+    nt = 1500
+    v = (rng.normal(size=(nt, 3, 3)) * 10).astype(np.float32)
+    v[:, 1] = v[:, 0] + (rng.normal(size=(nt, 3)) * 1.5).astype(np.float32)
+    v[:, 2] = v[:, 0] + (rng.normal(size=(nt, 3)) * 1.5).astype(np.float32)
+    v[:40, 2] = v[:40, 1]                      # zero-area: two equal vertices
+    v[40:80, 1] = v[40:80, 0]; v[40:80, 2] = v[40:80, 0]  # a point
+    v[80:200, :, 1] = np.round(v[80:200, :1, 1])  # axis-aligned (flat in y, on integer planes): zero-thickness boxes
+    v[200:260, :, 0] = 0.0                       # lying in the x = 0 plane
+    v[260:300] = v[300:340]                      # exact duplicates
+    v *= np.float32(scale)
+    verts = np.concatenate([v.reshape(-1, 3), np.ones((nt * 3, 1), dtype=np.float32)], axis=1)
+    idx = np.arange(nt * 3, dtype=np.int32)
+    m = rtb200.Mesh().set(verts, idx).finish()
+    A = m.arrays()
+    b = rtb200.FlatBVH.build(m)
+    ctx.upload_scene(A, b.nodes, b.tri_indices)
+    sc = O.OracleScene(A, b.nodes, b.tri_indices)
+    n = 40000
+    rays = np.zeros((n, 8), dtype=np.float32)
+    rays[:, 0:3] = (rng.normal(size=(n, 3)) * 12 * scale).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 4:7] = d
+    rays[:, 3] = rtb200.T_INIT
+    k = n // 8
+    rays[:k, 4:7] = 0; rays[:k, 4 + (np.arange(k) % 3)] = np.where(np.arange(k) % 2, 1.0, -1.0)   # along an axis
+    rays[k:2 * k, 5] = 0.0                                         # one zero component
+    rays[2 * k:2 * k + 500, 5] = -0.0                              # negative zero
+    rays[3 * k:4 * k, 0:3] = np.round(rays[3 * k:4 * k, 0:3] / scale) * scale  # origins on integer planes (on box faces)
+    rays[4 * k:5 * k, 3] = (rng.random(k) * 20 * scale + 1e-3).astype(np.float32)  # finite tmax
+    for mode in (rtb200.CLOSEST, rtb200.ANY):
+        want, _ = sc.trace(mode, rays)
+        assert (want["idx"] >= 0).mean() > 0.02
+        for sched in (0, 1):
+            ctx.set_option("scheduler", sched)
+            assert_hits_identical(ctx.trace(mode, rays), want, f"seed {seed} scale {scale} mode {mode} scheduler {sched}")
+    ctx.set_option("scheduler", -1)
+
+
 def test_band_partition_covers_frame(ctx):
     """interleaved row bands (the multi-GPU partition) of the fused primary + frame kernels tile the frame exactly"""
     import torch
