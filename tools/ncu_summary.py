@@ -8,7 +8,9 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'l1tex__t_bytes.sum',
+KEYS = ['gpu__time_duration.sum', 'SM_B.TriageCompute.l1tex__t_sectors.sum', 'SM_B.TriageCompute.l1tex__t_sectors_lookup_hit.sum',
+        'SM_B.TriageCompute.l1tex__t_sectors_lookup_miss.sum', 'derived__l1tex__lsu_writeback_bytes_mem_lgds.sum.per_second',
+        'lts__t_sectors.sum', 'lts__t_sectors_op_read.sum', 'lts__t_sectors_srcunit_tex.sum', 'sm__cycles_active.avg', 'sm__cycles_elapsed.avg', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'l1tex__t_bytes.sum',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'smsp__inst_executed.sum', 'l1tex__t_sector_hit_rate.pct',
         'lts__t_sector_hit_rate.pct', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
