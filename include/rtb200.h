@@ -125,6 +125,10 @@ int rt_primary(rt_context* ctx, int w, int h, rt_hit* hits_host);
 
 /* ---- device-resident variants (benchmarks, multi-GPU plumbing; pointers are device memory) ---- */
 int rt_trace_device(rt_context* ctx, int mode, int64_t n, const rt_ray* d_rays, rt_hit* d_hits);
+/* Same results as rt_trace_device, ray for ray and bit for bit, but the batch is traced in coherence order (key =
+ * direction octant | Morton code of the origin | coarse direction; radix sort, gather, trace, scatter back): an optional
+ * pre-pass for large incoherent batches. n < 2^31. */
+int rt_trace_sorted_device(rt_context* ctx, int mode, int64_t n, const rt_ray* d_rays, rt_hit* d_hits);
 /* Primary rays of a w x h frame generated in-kernel from the Params block (vR.cl:1156-1196) and
  * traced closest-hit; pixel i = y*w+x. Pixels failing the scene-AABB gate get idx = -1,
  * t = RT_T_INIT. d_rays_out (optional, may be NULL) receives the generated rays. Only rows

@@ -407,6 +407,42 @@ __global__ void diffuse_rays_kernel(SceneView s, long long n, const float4* rays
     }
 }
 
+// ---- optional coherence pre-pass for ray buffers: sort key = direction octant | Morton code of the quantised origin |
+// coarse direction. Tracing the rays in key order changes nothing per ray (results are scattered back to the caller's
+// order) but puts rays that walk the same part of the tree into the same warp.
+__device__ __forceinline__ unsigned int spread3(unsigned int v) {  // 10 bits -> every third bit
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void ray_sort_keys_kernel(long long n, const float4* rays, float3 lo, float3 inv_extent, unsigned int* keys, unsigned int* index) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = rays[2 * i], d = rays[2 * i + 1];
+    const unsigned int octant = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+    const float qx = fminf(fmaxf((o.x - lo.x) * inv_extent.x, 0.f), 0.999f), qy = fminf(fmaxf((o.y - lo.y) * inv_extent.y, 0.f), 0.999f),
+                qz = fminf(fmaxf((o.z - lo.z) * inv_extent.z, 0.f), 0.999f);
+    const unsigned int morton = spread3((unsigned int)(qx * 128.f)) | (spread3((unsigned int)(qy * 128.f)) << 1) |
+                                (spread3((unsigned int)(qz * 128.f)) << 2);  // 21 bits
+    const unsigned int dx = (unsigned int)(fminf(fabsf(d.x), 0.999f) * 4.f), dy = (unsigned int)(fminf(fabsf(d.y), 0.999f) * 4.f),
+                       dz = (unsigned int)(fminf(fabsf(d.z), 0.999f) * 4.f);
+    keys[i] = (octant << 27) | (morton << 6) | (dx << 4) | (dy << 2) | dz;
+    index[i] = (unsigned int)i;
+}
+__global__ void ray_gather_kernel(long long n, const float4* rays, const unsigned int* perm, float4* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned int src = perm[i];
+    out[2 * i] = rays[2 * (size_t)src];
+    out[2 * i + 1] = rays[2 * (size_t)src + 1];
+}
+__global__ void hit_scatter_kernel(long long n, const float4* hits_sorted, const unsigned int* perm, float4* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[perm[i]] = hits_sorted[i];
+}
+
 // ---- self test: div_hoisted(x, d, div_prepare(d)) must equal x / d bit for bit over the admitted window ---
 // d: any sign, exponent in [-20, 20]; x: 0 or any sign, exponent in [-100, 61]; mantissas random or edge patterns.
 // Range probe: same comparison with the numerator's exponent fixed to `ex` (unbiased) and the divisor's exponent

@@ -3,6 +3,7 @@
 // 858-1005, 1222-1287, 2050-2433). No CPU fallback: every entry point needs a CUDA device.
 #include "../../include/rtb200.h"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 
@@ -31,6 +32,8 @@ struct rt_context {
     cudaStream_t out_stream = nullptr;    // device->host copies of rt_trace chunks
     cudaEvent_t out_events[16] = {nullptr};
     cudaEvent_t wf_events[6] = {nullptr};
+    void* d_sort = nullptr;               // ray-sorting scratch (keys, permutation, sorted rays, sorted hits, cub temp)
+    size_t sort_bytes = 0;
     void* d_wf = nullptr;                 // wavefront scratch: path state + ray queues + counters
     size_t wf_bytes = 0;
     // scene
@@ -157,6 +160,7 @@ extern "C" int rt_destroy(rt_context* ctx) {
     for (auto& ev : ctx->wf_events)
         if (ev) cudaEventDestroy(ev);
     cudaFree(ctx->d_wf);
+    cudaFree(ctx->d_sort);
     if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -431,6 +435,56 @@ static int do_trace_device(rt_context* ctx, int mode, long long n, const rt_ray*
     return rc;
 }
 
+static int ensure(rt_context* ctx, void** p, size_t* have, size_t need) {
+    if (*have >= need) return RT_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    CK(ctx, cudaMalloc(p, need));
+    *have = need;
+    return RT_OK;
+}
+
+// Trace a ray buffer in coherence order: key generation -> radix sort -> gather -> trace -> scatter the hits back to
+// the caller's order. Per-ray results are those of rt_trace_device, bit for bit; only the order of execution changes.
+extern "C" int rt_trace_sorted_device(rt_context* ctx, int mode, int64_t n, const rt_ray* d_rays, rt_hit* d_hits) {
+    int rc = require(ctx, false, false);
+    if (rc) return rc;
+    if ((mode != RT_CLOSEST && mode != RT_ANY) || n < 0 || n > 0x7fffffff || (n > 0 && (!d_rays || !d_hits)))
+        return set_err(ctx, RT_E_INVALID, "rt_trace_sorted_device: bad arguments");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return RT_OK;
+    const size_t N = (size_t)n, npad = (N + 63) & ~(size_t)63;
+    size_t tmp = 0;
+    CK(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned int*)nullptr, (unsigned int*)nullptr, (unsigned int*)nullptr,
+                                            (unsigned int*)nullptr, (int)n, 0, 30, ctx->stream));
+    tmp = (tmp + 255) & ~(size_t)255;
+    const size_t need = 16 * npad + 32 * npad + 16 * npad + tmp;  // 4 x u32 arrays, sorted rays, sorted hits, cub temp
+    if ((rc = ensure(ctx, &ctx->d_sort, &ctx->sort_bytes, need))) return rc;
+    uint8_t* base = (uint8_t*)ctx->d_sort;
+    unsigned int *keys_in = (unsigned int*)base, *keys_out = keys_in + npad, *idx_in = keys_out + npad, *perm = idx_in + npad;
+    float4* sorted_rays = (float4*)(base + 16 * npad);
+    float4* sorted_hits = (float4*)(base + 48 * npad);
+    void* cub_tmp = base + 64 * npad;
+    const float3 lo = make_float3(ctx->hdr.root_min[0], ctx->hdr.root_min[1], ctx->hdr.root_min[2]);
+    float3 inv;
+    inv.x = 1.0f / fmaxf(ctx->hdr.root_max[0] - lo.x, 1e-20f);
+    inv.y = 1.0f / fmaxf(ctx->hdr.root_max[1] - lo.y, 1e-20f);
+    inv.z = 1.0f / fmaxf(ctx->hdr.root_max[2] - lo.z, 1e-20f);
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((N + threads - 1) / threads);
+    ray_sort_keys_kernel<<<blocks, threads, 0, ctx->stream>>>(n, (const float4*)d_rays, lo, inv, keys_in, idx_in);
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, keys_in, keys_out, idx_in, perm, (int)n, 0, 30, ctx->stream));
+    ray_gather_kernel<<<blocks, threads, 0, ctx->stream>>>(n, (const float4*)d_rays, perm, sorted_rays);
+    CK(ctx, cudaGetLastError());
+    if ((rc = do_trace_device(ctx, mode, n, (const rt_ray*)sorted_rays, (rt_hit*)sorted_hits))) return rc;
+    hit_scatter_kernel<<<blocks, threads, 0, ctx->stream>>>(n, sorted_hits, perm, (float4*)d_hits);
+    CK(ctx, cudaGetLastError());
+    ctx->counters[RT_CNT_KERNEL_LAUNCHES] += 3;
+    return RT_OK;
+}
+
 extern "C" int rt_trace_device(rt_context* ctx, int mode, int64_t n, const rt_ray* d_rays, rt_hit* d_hits) {
     int rc = require(ctx, false, false);
     if (rc) return rc;
@@ -441,15 +495,6 @@ extern "C" int rt_trace_device(rt_context* ctx, int mode, int64_t n, const rt_ra
     return do_trace_device(ctx, mode, n, d_rays, d_hits);
 }
 
-static int ensure(rt_context* ctx, void** p, size_t* have, size_t need) {
-    if (*have >= need) return RT_OK;
-    if (*p) cudaFree(*p);
-    *p = nullptr;
-    *have = 0;
-    CK(ctx, cudaMalloc(p, need));
-    *have = need;
-    return RT_OK;
-}
 
 // Device alias of a pinned (page-locked) host buffer, or nullptr for pageable memory.
 static void* pinned_alias(const void* host_ptr) {

@@ -31,7 +31,7 @@
 namespace rtb {
 
 static const uint32_t kBlobMagic = 0x42325452u;  // "RT2B"
-static const uint32_t kBlobVersion = 3;
+static const uint32_t kBlobVersion = 4;
 static const int32_t kRefPoison = (int32_t)0x80000000;
 
 struct BlobHeader {
@@ -48,7 +48,8 @@ struct BlobHeader {
     int32_t reserved0[1];
     uint64_t off_pairs, off_tris, off_verts, off_indices, off_normals, off_normal_indices, off_mat_diffuse,
         off_tri_to_material;
-    uint8_t pad[256 - 8 - 8 - 12 * 4 - 8 * 8];
+    float root_min[3], root_max[3];  // bounds of reference node 0 (used to quantise ray origins when sorting rays)
+    uint8_t pad[256 - 8 - 8 - 12 * 4 - 8 * 8 - 6 * 4];
 };
 static_assert(sizeof(BlobHeader) == 256, "header is one 256-byte block");
 

@@ -166,6 +166,10 @@ int pack_scene(const SceneInputs& in, int top_pairs, uint8_t** out_blob, uint64_
         check(c0.mn); check(c0.mx); check(c1.mn); check(c1.mx);
     }
     h.coords_in_window = in_window ? 1 : 0;
+    for (int k = 0; k < 3; k++) {
+        h.root_min[k] = nodes[0].mn[k];
+        h.root_max[k] = nodes[0].mx[k];
+    }
 
     // ---- triangles in tri_indices order; `last` set from the leaves
     float* tris = (float*)(blob + h.off_tris);

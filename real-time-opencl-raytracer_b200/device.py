@@ -19,7 +19,7 @@ HIT_DTYPE = np.dtype([("idx", np.int32), ("t", np.float32), ("u", np.float32), (
 
 ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_version", "rt_set_stream", "rt_synchronize", "rt_upload_scene",
-    "rt_scene_blob", "rt_copy_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_primary", "rt_trace_device",
+    "rt_scene_blob", "rt_copy_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_primary", "rt_trace_device", "rt_trace_sorted_device",
     "rt_primary_device", "rt_primary_gather_device", "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free",
     "rt_memcpy_to_host", "rt_host_register", "rt_host_unregister", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
     "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest", "rt_selftest_range", "rt_pack_scene_host", "rt_free_host",
@@ -53,6 +53,7 @@ def lib():
         L.rt_trace.argtypes = [vp, i32, i64, vp, vp]
         L.rt_trace_device.argtypes = [vp, i32, i64, vp, vp]
         L.rt_primary.argtypes = [vp, i32, i32, vp]
+        L.rt_trace_sorted_device.argtypes = [vp, i32, i64, vp, vp]
         L.rt_primary_device.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
         L.rt_shadow_device.argtypes = [vp, i64, vp, vp, vp, vp]
         L.rt_primary_gather_device.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
@@ -238,6 +239,10 @@ class Context:
     # --- hot path, device buffers (torch tensors or raw device pointers) ---
     def trace_device(self, mode, n, d_rays, d_hits):
         self._ck(lib().rt_trace_device(self._h, mode, n, _ptr(d_rays), _ptr(d_hits)))
+
+    def trace_sorted_device(self, mode, n, d_rays, d_hits):
+        """rt_trace_device with the coherence-sorting pre-pass (same results, different execution order)"""
+        self._ck(lib().rt_trace_sorted_device(self._h, mode, n, _ptr(d_rays), _ptr(d_hits)))
 
     def primary_device(self, w, h, d_hits, d_rays_out=None, part=0, n_parts=1, band_rows=4):
         self._ck(lib().rt_primary_device(self._h, w, h, part, n_parts, band_rows, _ptr(d_hits), _ptr(d_rays_out)))

@@ -277,6 +277,32 @@ def test_random_triangle_soup_fuzz(ctx, seed, scale):
     ctx.set_option("scheduler", -1)
 
 
+def test_sorted_trace_gives_the_same_hits(ctx):
+    """rt_trace_sorted_device (coherence pre-pass) == rt_trace_device, ray for ray"""
+    import torch
+
+    g = load_scene("mix")
+    _upload(ctx, g)
+    rays = np.tile(g["random_rays"], (40, 1))
+    rng = np.random.default_rng(0)
+    rays = rays[rng.permutation(rays.shape[0])].copy()
+    n = rays.shape[0]
+    d_r = torch.from_numpy(rays).cuda()
+    for mode in (rtb200.CLOSEST, rtb200.ANY):
+        a, b = torch.zeros((n, 4), device="cuda"), torch.zeros((n, 4), device="cuda")
+        ctx.trace_device(mode, n, d_r, a)
+        ctx.trace_sorted_device(mode, n, d_r, b)
+        ctx.synchronize()
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+    # and small / ragged batches
+    for m in (1, 33, 1000):
+        a, b = torch.zeros((m, 4), device="cuda"), torch.zeros((m, 4), device="cuda")
+        ctx.trace_device(rtb200.CLOSEST, m, d_r, a)
+        ctx.trace_sorted_device(rtb200.CLOSEST, m, d_r, b)
+        ctx.synchronize()
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+
+
 def test_band_partition_covers_frame(ctx):
     """interleaved row bands (the multi-GPU partition) of the fused primary + frame kernels tile the frame exactly"""
     import torch

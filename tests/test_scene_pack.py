@@ -11,7 +11,7 @@ from oracle import oracle_py as O
 HDR = np.dtype([("magic", "<u4"), ("version", "<u4"), ("total_bytes", "<u8"), ("root_ref", "<i4"), ("num_pairs", "<i4"),
                 ("num_tris", "<i4"), ("top_pairs", "<i4"), ("max_depth", "<i4"), ("V", "<i4"), ("T", "<i4"), ("Vn", "<i4"),
                 ("M", "<i4"), ("num_ref_nodes", "<i4"), ("coords_in_window", "<i4"), ("reserved", "<i4"),
-                ("off", "<u8", 8)])
+                ("off", "<u8", 8), ("root_min", "<f4", 3), ("root_max", "<f4", 3)])
 POISON = -(2 ** 31)
 TMIN = np.float32(0.001)
 

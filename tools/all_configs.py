@@ -129,6 +129,8 @@ def run_scene(tag, mesh, w, h, light=(-23.0, 200.0, 3.0), d_radius=0.0, d_beta=0
             a_bytes = (64 * cnt_d["inner"] + 48 * cnt_d["tris"]) / dsel.size + 48
             r[f"diffuse_4spp_{name}"] = {"ms": ms, "mrays_s": nd / ms / 1e3, "rays": nd, "algorithmic_GBps": a_bytes * nd / ms / 1e6}
         ctx.set_option("scheduler", -1)
+        ms = timeit(lambda: ctx.trace_sorted_device(rtb200.CLOSEST, nd, d_dr, d_dh), iters=6)
+        r["diffuse_4spp_lanes_with_sort_prepass"] = {"ms_incl_sort_gather_scatter": ms, "mrays_s": nd / ms / 1e3}
         del d_dr, d_dh
     # ---- frame ----
     d_img = torch.zeros((h, w), dtype=torch.int32, device="cuda")
