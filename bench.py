@@ -547,6 +547,25 @@ def extra_passes(ctx, torch, rtb200, w, h, stream):
     ctx.set_option("frame_mode", 0)
     out["full_frame_megakernel_ms"] = timed(lambda: ctx.render_frame_device(w, h, d_img), iters=5)
     ctx.set_option("frame_mode", 1)
+    # the frame through the host entry points (pinned frame buffers, wall clock over 50 frames, params set every frame)
+    import time
+    bufs = [torch.zeros((h, w), dtype=torch.int32).pin_memory() for _ in range(2)]
+    nf = 50
+    for _ in range(3):
+        ctx.render_frame(w, h, bufs[0])
+    t0 = time.perf_counter()
+    for k in range(nf):
+        ctx.set_params(ctx_params[0])
+        ctx.render_frame(w, h, bufs[0])
+    out["frame_e2e_ms_frame_by_frame"] = (time.perf_counter() - t0) / nf * 1e3
+    t0 = time.perf_counter()
+    for k in range(nf):
+        ctx.set_params(ctx_params[0])
+        ctx.render_frame_begin(w, h, bufs[k & 1], k & 1)
+        if k:
+            ctx.render_frame_end((k - 1) & 1)
+    ctx.render_frame_end((nf - 1) & 1)
+    out["frame_e2e_ms_two_in_flight"] = (time.perf_counter() - t0) / nf * 1e3
     # NOT the shipped default: closest-hit traversal with the reciprocal-multiply box test (not bit-exact)
     ctx.set_option("fast_box", 1)
     ms = timed(lambda: ctx.primary_device(w, h, d_hits))

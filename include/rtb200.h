@@ -113,6 +113,15 @@ int rt_set_params(rt_context* ctx, const float params[32]);
  * w*h uint32 pixels, row-major, pixel = (b<<16)|(g<<8)|r as rgbToInt (vR.cl:186-195).
  * Replaces raytrace_gpgpu() (RayTracer.cpp:330-344). */
 int rt_render_frame(rt_context* ctx, int w, int h, uint32_t* out_host);
+/* The same frame without the per-frame stall of displayGL()'s clFinish + blocking read (RayTracer.cpp:284-293,
+ * 341-343): _begin enqueues the frame described by the last rt_set_params into out_host and returns; _end blocks
+ * until the frame of that slot is complete in out_host. Up to RT_FRAME_SLOTS frames may be in flight, one per slot;
+ * rt_set_params for the next frame may be called at once (every launch carries its Params block by value).
+ * out_host must stay valid until _end: page-locked memory (rt_host_register, cudaHostAlloc) receives the pixels
+ * straight from the kernel while the next frame traces; pageable memory is filled by a copy inside _end. */
+#define RT_FRAME_SLOTS 4
+int rt_render_frame_begin(rt_context* ctx, int w, int h, uint32_t* out_host, int slot);
+int rt_render_frame_end(rt_context* ctx, int slot);
 
 /* Batch operator = traverse_bvh (vR.cl:658-1010) on n caller-supplied rays; host buffers. */
 int rt_trace(rt_context* ctx, int mode, int64_t n, const rt_ray* rays_host, rt_hit* hits_host);

@@ -32,6 +32,8 @@ struct rt_context {
     cudaStream_t out_stream = nullptr;    // device->host copies of rt_trace chunks
     cudaEvent_t out_events[16] = {nullptr};
     cudaEvent_t wf_events[6] = {nullptr};
+    // frames in flight (rt_render_frame_begin / _end)
+    struct FrameSlot { cudaEvent_t done = nullptr; bool pending = false; void* d_out = nullptr; size_t d_bytes = 0; uint32_t* host = nullptr; size_t bytes = 0; } slots[RT_FRAME_SLOTS];
     void* d_sort = nullptr;               // ray-sorting scratch (keys, permutation, sorted rays, sorted hits, cub temp)
     size_t sort_bytes = 0;
     void* d_wf = nullptr;                 // wavefront scratch: path state + ray queues + counters
@@ -127,6 +129,7 @@ extern "C" int rt_create(int device_ordinal, rt_context** out_ctx) {
     for (auto& ev : ctx->chunk_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : ctx->out_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : ctx->wf_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& sl : ctx->slots) CK(nullptr, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     CK(nullptr, cudaMalloc(&ctx->d_counter, 256));
     memset(&ctx->hdr, 0, sizeof ctx->hdr);
     memset(&ctx->view, 0, sizeof ctx->view);
@@ -159,6 +162,10 @@ extern "C" int rt_destroy(rt_context* ctx) {
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->wf_events)
         if (ev) cudaEventDestroy(ev);
+    for (auto& sl : ctx->slots) {
+        if (sl.done) cudaEventDestroy(sl.done);
+        cudaFree(sl.d_out);
+    }
     cudaFree(ctx->d_wf);
     cudaFree(ctx->d_sort);
     if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
@@ -876,6 +883,46 @@ extern "C" int rt_render_frame(rt_context* ctx, int w, int h, uint32_t* out_host
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->counters[RT_CNT_H2D_BYTES] += sizeof(ParamsBlock);
     ctx->counters[RT_CNT_D2H_BYTES] += bytes;
+    return RT_OK;
+}
+
+// Pipelined frames: begin enqueues, end waits. Each launch carries its Params block by value, so rt_set_params for
+// frame k+1 may be called while frame k is still in flight.
+extern "C" int rt_render_frame_begin(rt_context* ctx, int w, int h, uint32_t* out_host, int slot) {
+    int rc = require(ctx, true, true);
+    if (rc) return rc;
+    if (!out_host || w <= 0 || h <= 0) return set_err(ctx, RT_E_INVALID, "rt_render_frame_begin: bad arguments");
+    if (slot < 0 || slot >= RT_FRAME_SLOTS) return set_err(ctx, RT_E_INVALID, "rt_render_frame_begin: slot %d outside 0..%d", slot, RT_FRAME_SLOTS - 1);
+    rt_context::FrameSlot& sl = ctx->slots[slot];
+    if (sl.pending) return set_err(ctx, RT_E_INVALID, "rt_render_frame_begin: slot %d still has a frame in flight (call rt_render_frame_end first)", slot);
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)w * h * 4;
+    void* alias = ctx->opt_zero_copy ? pinned_alias(out_host) : nullptr;
+    if (alias) {
+        if ((rc = rt_render_frame_device(ctx, w, h, 0, 1, 4, (uint32_t*)alias))) return rc;
+        sl.host = nullptr;
+    } else {  // pageable destination: per-slot device frame, copied out by rt_render_frame_end
+        if ((rc = ensure(ctx, &sl.d_out, &sl.d_bytes, bytes))) return rc;
+        if ((rc = rt_render_frame_device(ctx, w, h, 0, 1, 4, (uint32_t*)sl.d_out))) return rc;
+        sl.host = out_host;
+    }
+    sl.bytes = bytes;
+    CK(ctx, cudaEventRecord(sl.done, ctx->stream));
+    sl.pending = true;
+    return RT_OK;
+}
+
+extern "C" int rt_render_frame_end(rt_context* ctx, int slot) {
+    if (!ctx) return RT_E_INVALID;
+    if (slot < 0 || slot >= RT_FRAME_SLOTS) return set_err(ctx, RT_E_INVALID, "rt_render_frame_end: slot %d outside 0..%d", slot, RT_FRAME_SLOTS - 1);
+    rt_context::FrameSlot& sl = ctx->slots[slot];
+    if (!sl.pending) return set_err(ctx, RT_E_INVALID, "rt_render_frame_end: no frame in flight in slot %d", slot);
+    CK(ctx, cudaSetDevice(ctx->device));
+    sl.pending = false;
+    CK(ctx, cudaEventSynchronize(sl.done));
+    if (sl.host) CK(ctx, cudaMemcpy(sl.host, sl.d_out, sl.bytes, cudaMemcpyDeviceToHost));
+    ctx->counters[RT_CNT_H2D_BYTES] += sizeof(ParamsBlock);
+    ctx->counters[RT_CNT_D2H_BYTES] += sl.bytes;
     return RT_OK;
 }
 

@@ -19,7 +19,7 @@ HIT_DTYPE = np.dtype([("idx", np.int32), ("t", np.float32), ("u", np.float32), (
 
 ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_version", "rt_set_stream", "rt_synchronize", "rt_upload_scene",
-    "rt_scene_blob", "rt_copy_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_trace", "rt_primary", "rt_trace_device", "rt_trace_sorted_device",
+    "rt_scene_blob", "rt_copy_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_render_frame_begin", "rt_render_frame_end", "rt_trace", "rt_primary", "rt_trace_device", "rt_trace_sorted_device",
     "rt_primary_device", "rt_primary_gather_device", "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free",
     "rt_memcpy_to_host", "rt_host_register", "rt_host_unregister", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
     "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest", "rt_selftest_range", "rt_pack_scene_host", "rt_free_host",
@@ -50,6 +50,8 @@ def lib():
         L.rt_copy_scene_blob.argtypes = [vp, vp, C.c_size_t]
         L.rt_set_params.argtypes = [vp, vp]
         L.rt_render_frame.argtypes = [vp, i32, i32, vp]
+        L.rt_render_frame_begin.argtypes = [vp, i32, i32, vp, i32]
+        L.rt_render_frame_end.argtypes = [vp, i32]
         L.rt_trace.argtypes = [vp, i32, i64, vp, vp]
         L.rt_trace_device.argtypes = [vp, i32, i64, vp, vp]
         L.rt_primary.argtypes = [vp, i32, i32, vp]
@@ -221,6 +223,14 @@ class Context:
             out = np.empty((h, w), dtype=np.uint32)
         self._ck(lib().rt_render_frame(self._h, w, h, _ptr(out)))
         return out
+
+    def render_frame_begin(self, w, h, out, slot=0):
+        """enqueue the frame of the last set_params() into `out` (numpy uint32 (h, w) or pinned torch tensor, kept alive
+        by the caller until render_frame_end(slot)) and return without waiting"""
+        self._ck(lib().rt_render_frame_begin(self._h, w, h, _ptr(out), slot))
+
+    def render_frame_end(self, slot=0):
+        self._ck(lib().rt_render_frame_end(self._h, slot))
 
     def trace(self, mode, rays, hits=None):
         n = rays.shape[0] if isinstance(rays, np.ndarray) else rays.numel() * rays.element_size() // 32

@@ -78,17 +78,86 @@ int RayTracer::updateCamera() {
     return SDK_SUCCESS;
 }
 
+void RayTracer::unpin(std::vector<unsigned int>& v) {
+    for (size_t i = 0; i < pinned_.size(); i++)
+        if (pinned_[i].first == (void*)v.data()) {
+            if (ctx_) rt_host_unregister(ctx_, pinned_[i].first);
+            pinned_.erase(pinned_.begin() + i);
+            return;
+        }
+}
+
+bool RayTracer::size_and_pin(std::vector<unsigned int>& v) {
+    const size_t n = (size_t)image_width * image_height;
+    if (v.size() != n) {
+        unpin(v);  // before the vector frees the pages
+        v.assign(n, 0u);
+    }
+    for (const auto& p : pinned_)
+        if (p.first == (void*)v.data()) return true;
+    void* alias = nullptr;
+    if (n == 0 || rt_host_register(ctx_, v.data(), n * sizeof(unsigned int), &alias) != RT_OK) return false;  // pageable still works
+    pinned_.push_back({(void*)v.data(), n * sizeof(unsigned int)});
+    return true;
+}
+
 int RayTracer::raytrace_gpgpu() {
-    out_data.resize((size_t)image_width * image_height);
-    if (!ctx_ || rt_render_frame(ctx_, image_width, image_height, out_data.data()) != RT_OK) {
-        err_ = ctx_ ? rt_last_error(ctx_) : "raytrace_gpgpu before setupCL";
+    if (!ctx_) {
+        err_ = "raytrace_gpgpu before setupCL";
+        return SDK_FAILURE;
+    }
+    while (inflight_ > 0)
+        if (raytrace_gpgpu_end() != SDK_SUCCESS) return SDK_FAILURE;
+    size_and_pin(out_data);
+    if (rt_render_frame(ctx_, image_width, image_height, out_data.data()) != RT_OK) {
+        err_ = rt_last_error(ctx_);
         return SDK_FAILURE;
     }
     return SDK_SUCCESS;
 }
 
+int RayTracer::raytrace_gpgpu_begin() {
+    if (!ctx_) {
+        err_ = "raytrace_gpgpu_begin before setupCL";
+        return SDK_FAILURE;
+    }
+    if (inflight_ >= 2) {
+        err_ = "raytrace_gpgpu_begin: two frames already in flight";
+        return SDK_FAILURE;
+    }
+    const int slot = (head_ + inflight_) & 1;
+    size_and_pin(ring_[slot]);
+    if (rt_render_frame_begin(ctx_, image_width, image_height, ring_[slot].data(), slot) != RT_OK) {
+        err_ = rt_last_error(ctx_);
+        return SDK_FAILURE;
+    }
+    inflight_++;
+    return SDK_SUCCESS;
+}
+
+int RayTracer::raytrace_gpgpu_end() {
+    if (!ctx_ || inflight_ < 1) {
+        err_ = "raytrace_gpgpu_end: no frame in flight";
+        return SDK_FAILURE;
+    }
+    const int slot = head_;
+    head_ ^= 1;
+    inflight_--;
+    if (rt_render_frame_end(ctx_, slot) != RT_OK) {
+        err_ = rt_last_error(ctx_);
+        return SDK_FAILURE;
+    }
+    out_data.swap(ring_[slot]);  // both stay page-locked: registration follows the pages, not the vector
+    return SDK_SUCCESS;
+}
+
 int RayTracer::cleanup() {
-    if (ctx_) rt_destroy(ctx_);
+    if (ctx_) {
+        while (inflight_ > 0) raytrace_gpgpu_end();
+        for (const auto& p : pinned_) rt_host_unregister(ctx_, p.first);
+        pinned_.clear();
+        rt_destroy(ctx_);
+    }
     ctx_ = nullptr;
     return SDK_SUCCESS;
 }

@@ -13,6 +13,7 @@
 // All device work goes through the C ABI of include/rtb200.h (librtb200.so); no OpenCL, no CPU fallback.
 #pragma once
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "BVH_Cuda.h"
@@ -54,6 +55,13 @@ public:
     int initRayTraceFromMesh(const char* flat_bvh_cache = nullptr);
     int updateCamera();
     int raytrace_gpgpu();
+    // The same frame without the reference's per-frame stall (clFinish + blocking read, RayTracer.cpp:341-343):
+    // _begin enqueues the frame of the last updateCamera() and returns, _end waits for the oldest frame in flight and
+    // leaves it in out_data. Two frames may be in flight, so the host updates the camera / consumes frame k while the
+    // device traces frame k+1.
+    int raytrace_gpgpu_begin();
+    int raytrace_gpgpu_end();
+    int frames_in_flight() const { return inflight_; }
     int cleanup();
 
     bool write_ppm(const char* path) const;  // headless replacement of the GLUT texture blit
@@ -63,6 +71,11 @@ public:
 
 private:
     int upload();
+    bool size_and_pin(std::vector<unsigned int>& v);  // w*h pixels, page-locked so the kernel stores into it directly
+    void unpin(std::vector<unsigned int>& v);
+    std::vector<std::pair<void*, size_t>> pinned_;
+    std::vector<unsigned int> ring_[2];
+    int head_ = 0, inflight_ = 0;
     rt_context* ctx_ = nullptr;
     std::string err_;
     double build_seconds_ = 0.0;

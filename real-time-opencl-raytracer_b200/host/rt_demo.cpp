@@ -1,13 +1,23 @@
 // rt_demo.cpp -- headless version of the reference's main() (RayTracer.cpp:574-606): set up the device,
 // load / generate a scene, build the SBVH, render `frames` frames of the orbit animation, write a PPM.
 //   rt_demo [scene.dae | terrain:<quads> | spheres:<subdiv>] [w h] [frames] [out.ppm]
+// The loop runs twice: frame by frame as the reference does (update camera, trace, wait, read back), then pipelined
+// with two frames in flight (RayTracer::raytrace_gpgpu_begin/_end).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "RayTracer.h"
 #include "SceneGen.h"
+
+// the host-side consumer of a finished frame (stands in for the reference's texture upload + blit, RayTracer.cpp:436-470)
+static unsigned long long consume(const std::vector<unsigned int>& frame, unsigned long long acc) {
+    unsigned long long s = 0;
+    for (unsigned int p : frame) s += p;
+    return acc * 1099511628211ull + s;
+}
 
 int main(int argc, char** argv) {
     const char* scene = argc > 1 ? argv[1] : "terrain:200";
@@ -41,15 +51,44 @@ int main(int argc, char** argv) {
            rt.last_build_seconds());
     rt.animate = true;
     rt.delta_t = 0.05f;
+    unsigned long long sum_a = 0, sum_b = 0;
+    const Camera start = rt.cam;  // both loops fly the same orbit
     const auto t0 = std::chrono::steady_clock::now();
     for (int f = 0; f < frames; f++) {
         if (rt.updateCamera() != SDK_SUCCESS || rt.raytrace_gpgpu() != SDK_SUCCESS) {
             fprintf(stderr, "frame %d failed: %s\n", f, rt.last_error().c_str());
             return 1;
         }
+        sum_a = consume(rt.out_data, sum_a);
     }
     const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    printf("%d frames %dx%d in %.3f s -> %.1f fps\n", frames, rt.image_width, rt.image_height, s, frames / s);
+    printf("%d frames %dx%d in %.3f s -> %.1f fps (frame by frame)\n", frames, rt.image_width, rt.image_height, s, frames / s);
+    rt.cam = start;
+    const auto t1 = std::chrono::steady_clock::now();
+    for (int f = 0; f < frames; f++) {
+        if (rt.updateCamera() != SDK_SUCCESS || rt.raytrace_gpgpu_begin() != SDK_SUCCESS) {
+            fprintf(stderr, "pipelined frame %d failed: %s\n", f, rt.last_error().c_str());
+            return 1;
+        }
+        if (rt.frames_in_flight() == 2) {  // frame f-1 is consumed while frame f traces
+            if (rt.raytrace_gpgpu_end() != SDK_SUCCESS) {
+                fprintf(stderr, "pipelined frame %d failed: %s\n", f - 1, rt.last_error().c_str());
+                return 1;
+            }
+            sum_b = consume(rt.out_data, sum_b);
+        }
+    }
+    while (rt.frames_in_flight() > 0) {
+        if (rt.raytrace_gpgpu_end() != SDK_SUCCESS) {
+            fprintf(stderr, "pipelined drain failed: %s\n", rt.last_error().c_str());
+            return 1;
+        }
+        sum_b = consume(rt.out_data, sum_b);
+    }
+    const double s1 = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    printf("%d frames %dx%d in %.3f s -> %.1f fps (two frames in flight)\n", frames, rt.image_width, rt.image_height, s1, frames / s1);
+    printf("frame checksums: %016llx / %016llx %s\n", sum_a, sum_b, sum_a == sum_b ? "(identical)" : "(DIFFERENT)");
+    if (sum_a != sum_b) return 2;
     if (!rt.write_ppm(out)) fprintf(stderr, "cannot write %s\n", out);
     rt.cleanup();
     return 0;
