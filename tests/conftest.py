@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-SCENES = ["test0", "test1", "ico2", "terrain12", "sticks150", "mix"]
+SCENES = ["test0", "test1", "ico2", "terrain12", "sticks150", "mix", "cubes2"]
 
 
 def pytest_configure(config):

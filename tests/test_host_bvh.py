@@ -110,3 +110,18 @@ def test_collada_roundtrip(tmp_path):
         assert same_bits(A[k], B[k]), k
     assert np.allclose(A["materials"][0, 12:15], B["materials"][0, 12:15])
     assert same_bits(A["aabb_min"], B["aabb_min"]) and same_bits(A["aabb_max"], B["aabb_max"])
+
+
+REF_CUBES2 = "/root/reference/x64/Release/data/collada/cubes2.DAE"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CUBES2), reason="the reference tree is only mounted in the build container")
+def test_loader_on_the_reference_scene_file():
+    """the COLLADA file the reference itself loads (RayTracer.cpp:862) through the new loader reproduces the committed
+    fixture (tests/golden/scene_cubes2.npz): 23 392 triangles, 13 materials, the file's own normals"""
+    A = rtb200.Mesh().load_dae(REF_CUBES2).arrays()
+    g = load_scene("cubes2")
+    assert A["indices"].size // 3 == 23392 and A["materials"].shape[0] == 13
+    for key, gkey in (("verts", "verts"), ("indices", "indices"), ("normals", "normals"), ("normal_indices", "normal_indices"),
+                      ("materials", "materials"), ("tri_to_material", "tri_to_material")):
+        assert same_bits(np.asarray(A[key]), g[gkey]), key
