@@ -44,6 +44,7 @@ struct TraceArgs {
     const unsigned long long* n_in_ptr;
     float4* shade_queue;
     unsigned long long* n_shade;
+    float* coef_out;          // SRC_QUEUE + ANY_HIT (wavefront shadow stage): coef[pixel] += occluded && t > 0.025 ? 0.25 : 1
 };
 
 #ifndef RTB_MINB_BATCH

@@ -207,7 +207,10 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                 has_ray = false;
             }
         }
-        if (SRC == SRC_QUEUE) {  // hand every ray that finished with a hit to the shade stage (one atomicAdd per warp)
+        if (SRC == SRC_QUEUE && ANY_HIT) {  // shadow stage: one ray per pixel per stage, stages are stream-ordered
+            if (finished) a.coef_out[out_index] += (res.idx >= 0 && tHit > 0.025f) ? 0.25f : 1.0f;  // vR.cl:1444-1449
+            finished = false;
+        } else if (SRC == SRC_QUEUE) {  // hand every ray that finished with a hit to the shade stage (one atomicAdd per warp)
             const bool push = finished && res.idx >= 0;
             const unsigned pm = __ballot_sync(FULL, push);
             if (pm) {

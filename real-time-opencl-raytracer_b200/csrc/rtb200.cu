@@ -69,6 +69,7 @@ struct rt_context {
     int opt_inner_exit = 8;     // persistent lanes: leave the inner phase when fewer lanes than this still descend
     int opt_frame_mode = 1;     // rt_render_frame*: 1 = wavefront pipeline (wavefront.cuh), 0 = one-thread-per-pixel megakernel
     int opt_wf_lanes = 1;       // wavefront bounce stages: 1 = persistent-lanes trace + dense shade kernel, 0 = fused batch kernel
+    int opt_wf_shadow_lanes = 0; // wavefront shadow stages on the persistent-lanes scheduler: 0 = none, 1 = bounces 1-2, 2 = all
     int opt_wf_late_div = 1;    // wavefront: grids of the later (smaller) stages are divided by this
     int opt_wf_split = 0;       // wavefront: blocks per SM given to the shadow stream when it overlaps a trace stage (0 = full grids)
     int opt_fast_box = 0;       // 1 = approximate reciprocal/FMA box test for CLOSEST-hit batch kernels (NOT bit-exact; experiment)
@@ -284,6 +285,7 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     else if (!strcmp(name, "frame_mode")) ctx->opt_frame_mode = value ? 1 : 0;
     else if (!strcmp(name, "wf_lanes")) ctx->opt_wf_lanes = value ? 1 : 0;
     else if (!strcmp(name, "wf_late_div")) ctx->opt_wf_late_div = value < 1 ? 1 : value;
+    else if (!strcmp(name, "wf_shadow_lanes")) ctx->opt_wf_shadow_lanes = value;
     else if (!strcmp(name, "wf_split")) ctx->opt_wf_split = value < 0 ? 0 : value;
     else if (!strcmp(name, "fast_box")) ctx->opt_fast_box = value ? 1 : 0;
     else if (!strcmp(name, "tile_order")) ctx->opt_tile_order = value < 0 ? 0 : value;
@@ -776,8 +778,9 @@ static int render_wavefront(rt_context* ctx, const TraceArgs& ta, uint32_t* d_ou
     float4* refl[2] = {(float4*)(base + off_q), (float4*)(base + off_q + 32 * npad)};
     float4* shad[3] = {(float4*)(base + off_q + 64 * npad), (float4*)(base + off_q + 96 * npad), (float4*)(base + off_q + 128 * npad)};
     float4* shade_q = (float4*)(base + off_q + 160 * npad);
-    int occ_trace = 1, occ_bounce = 1, occ_shadow = 1, occ_lanes = 1;
+    int occ_trace = 1, occ_bounce = 1, occ_shadow = 1, occ_lanes = 1, occ_shadow_lanes = 1;
     if ((rc = blocks_per_sm(ctx, trace_lanes_kernel<SRC_QUEUE, false>, 0, &occ_lanes))) return rc;
+    if ((rc = blocks_per_sm(ctx, trace_lanes_kernel<SRC_QUEUE, true>, 0, &occ_shadow_lanes))) return rc;
     if ((rc = blocks_per_sm(ctx, wf_trace_shade_kernel<true>, 0, &occ_trace))) return rc;
     if ((rc = blocks_per_sm(ctx, wf_trace_shade_kernel<false>, 0, &occ_bounce))) return rc;
     if ((rc = blocks_per_sm(ctx, wf_shadow_kernel, 0, &occ_shadow))) return rc;
@@ -828,7 +831,21 @@ static int render_wavefront(rt_context* ctx, const TraceArgs& ta, uint32_t* d_ou
         sh.n_in = cnt + 11 + b;
         int sh_per_sm = (split > 0 && split < occ_shadow && b < 2) ? split : occ_shadow;
         if (b > 0) sh_per_sm = sh_per_sm / ctx->opt_wf_late_div > 0 ? sh_per_sm / ctx->opt_wf_late_div : 1;
-        wf_shadow_kernel<<<(unsigned)(sh_per_sm * ctx->num_sms), kBlockThreads, 0, s_shadow>>>(sh);
+        if (ctx->opt_wf_shadow_lanes > (b == 0 ? 1 : 0)) {
+            // the shadow rays of the later bounces end after very different numbers of steps: persistent lanes
+            TraceArgs la;
+            memset(&la, 0, sizeof la);
+            la.scene = a.scene;
+            la.rays_in = sh.rays_in;
+            la.n_in_ptr = sh.n_in;
+            la.coef_out = a.coef;
+            la.work_counter = sh.work_counter;
+            int per_sm = occ_shadow_lanes / (b > 0 ? ctx->opt_wf_late_div : 1);
+            if (per_sm < 1) per_sm = 1;
+            trace_lanes_kernel<SRC_QUEUE, true><<<(unsigned)(per_sm * ctx->num_sms), kBlockThreads, 0, s_shadow>>>(la, ctx->opt_refill, ctx->opt_inner_exit);
+        } else {
+            wf_shadow_kernel<<<(unsigned)(sh_per_sm * ctx->num_sms), kBlockThreads, 0, s_shadow>>>(sh);
+        }
         CK(ctx, cudaGetLastError());
         ctx->counters[RT_CNT_KERNEL_LAUNCHES] += 2;
     }
