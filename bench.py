@@ -331,6 +331,22 @@ def main():
         e2e_s = time.perf_counter() - t0
         e2e = {"value": rays_total * args.steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 128,
                "d2h_bytes_per_step": n_pix * 16, "call": "rt_set_params + rt_primary (host buffers, pinned)"}
+        # the same pass with the result the N > 1 runs deliver: the 4-byte/pixel hit-index framebuffer (the size of the
+        # reference's own per-frame readback, RayTracer.cpp:343), stored by the kernel straight into pinned host memory
+        idx_frame = torch.empty((h, w), dtype=torch.int32).pin_memory()
+        for _ in range(3):
+            ctx.primary_gather_device(w, h, None, idx_frame, part=0, n_parts=1, band_rows=BAND_ROWS)
+            ctx.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.set_params(params)
+            ctx.primary_gather_device(w, h, None, idx_frame, part=0, n_parts=1, band_rows=BAND_ROWS)
+            ctx.synchronize()
+        e2e_idx_s = time.perf_counter() - t0
+        if not np.array_equal(idx_frame.numpy().reshape(-1), pinned.numpy().view(np.int32)[:, 0]):
+            raise SystemExit("bench: hit-index framebuffer differs from the hit records")
+        e2e["index_frame"] = {"value": rays_total * args.steps / e2e_idx_s / 1e6, "unit": UNIT, "d2h_bytes_per_step": n_pix * 4,
+                              "call": "rt_set_params + rt_primary_gather_device (4-byte/pixel hit-index frame in pinned host memory): the result the N > 1 runs deliver"}
         ctx.set_stream(stream.cuda_stream)
     else:
         # N > 1: params from host each step, own bands traced, framebuffer gathered, rank 0 reads the frame back
