@@ -107,17 +107,7 @@ extern "C" const char* rt_version(void) { return "rtb200 0.1 (sm_100a)"; }
 
 extern "C" const char* rt_last_error(const rt_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-extern "C" int rt_create(int device_ordinal, rt_context** out_ctx) {
-    if (!out_ctx) return set_err(nullptr, RT_E_INVALID, "rt_create: out_ctx is NULL");
-    *out_ctx = nullptr;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0)
-        return set_err(nullptr, RT_E_NO_DEVICE, "rt_create: no CUDA device (%s); this library has no CPU fallback",
-                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-    if (device_ordinal < 0 || device_ordinal >= count)
-        return set_err(nullptr, RT_E_INVALID, "rt_create: device %d out of range [0,%d)", device_ordinal, count);
-    rt_context* ctx = new rt_context();
+static int init_context(rt_context* ctx, int device_ordinal) {
     ctx->device = device_ordinal;
     CK(nullptr, cudaSetDevice(device_ordinal));
     cudaDeviceProp prop;
@@ -134,6 +124,25 @@ extern "C" int rt_create(int device_ordinal, rt_context** out_ctx) {
     CK(nullptr, cudaMalloc(&ctx->d_counter, 256));
     memset(&ctx->hdr, 0, sizeof ctx->hdr);
     memset(&ctx->view, 0, sizeof ctx->view);
+    return RT_OK;
+}
+
+extern "C" int rt_create(int device_ordinal, rt_context** out_ctx) {
+    if (!out_ctx) return set_err(nullptr, RT_E_INVALID, "rt_create: out_ctx is NULL");
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_err(nullptr, RT_E_NO_DEVICE, "rt_create: no CUDA device (%s); this library has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device_ordinal < 0 || device_ordinal >= count)
+        return set_err(nullptr, RT_E_INVALID, "rt_create: device %d out of range [0,%d)", device_ordinal, count);
+    rt_context* ctx = new rt_context();
+    const int rc = init_context(ctx, device_ordinal);
+    if (rc) {  // the message is in g_create_error; release whatever was created
+        rt_destroy(ctx);
+        return rc;
+    }
     *out_ctx = ctx;
     return RT_OK;
 }
@@ -189,10 +198,26 @@ extern "C" int rt_synchronize(rt_context* ctx) {
     return RT_OK;
 }
 
+// A blob may arrive from another process (rt_adopt_scene_blob after a broadcast): every section the kernels will index
+// must lie inside the allocation before any pointer is derived from the header.
+static const char* header_problem(const BlobHeader& h, size_t bytes) {
+    if (h.num_pairs < 0 || h.num_tris < 0 || h.V < 0 || h.T < 0 || h.Vn < 0 || h.M < 0 || h.top_pairs < 0) return "negative count";
+    struct { uint64_t off, size; } sec[] = {
+        {h.off_pairs, 64ull * (uint64_t)h.num_pairs},       {h.off_tris, 48ull * ((uint64_t)h.num_tris + 1)},
+        {h.off_verts, 16ull * (uint64_t)h.V},                {h.off_indices, 12ull * (uint64_t)h.T},
+        {h.off_normals, 16ull * (uint64_t)h.Vn},             {h.off_normal_indices, h.Vn ? 12ull * (uint64_t)h.T : 0ull},
+        {h.off_mat_diffuse, 16ull * (uint64_t)h.M},          {h.off_tri_to_material, h.M ? 4ull * (uint64_t)h.T : 0ull}};
+    for (const auto& s : sec)
+        if (s.off < sizeof(BlobHeader) || (s.off & 255u) || s.off > bytes || s.size > bytes - s.off) return "section outside the allocation";
+    if (h.root_ref >= 0 ? h.root_ref >= h.num_pairs : (h.root_ref != kRefPoison && ~h.root_ref > h.num_tris)) return "root reference out of range";
+    return nullptr;
+}
+
 static int bind_blob(rt_context* ctx, const BlobHeader& h, uint8_t* d_blob, size_t bytes, bool owned) {
     if (h.magic != kBlobMagic || h.version != kBlobVersion || h.total_bytes != bytes)
         return set_err(ctx, RT_E_INVALID, "scene blob header mismatch (magic %08x version %u bytes %llu vs %zu)", h.magic,
                        h.version, (unsigned long long)h.total_bytes, bytes);
+    if (const char* why = header_problem(h, bytes)) return set_err(ctx, RT_E_INVALID, "scene blob header rejected: %s", why);
     free_scene(ctx);
     ctx->d_blob = d_blob;
     ctx->blob_bytes = bytes;

@@ -524,6 +524,18 @@ def test_scene_blob_adopt_roundtrip(ctx):
     c2 = rtb200.Context(0)
     c2.adopt_scene_blob(moved.data_ptr(), nbytes)
     assert_hits_identical(c2.trace(rtb200.ANY, g["random_rays"]), g["random_hits_any"].view(HIT).reshape(-1), "adopted blob")
+    # a header whose sections do not fit the allocation is rejected before any pointer is derived from it
+    hdr = moved[:256].cpu().numpy().copy()
+    for field_offset, value in ((64, nbytes), (72, 2**40), (20, 2**30), (16, 2**30)):  # off_pairs, off_tris, num_pairs, root_ref
+        bad = moved.clone()
+        h2 = hdr.copy()
+        h2[field_offset:field_offset + 8 if field_offset >= 64 else field_offset + 4] = np.frombuffer(
+            (np.uint64(value) if field_offset >= 64 else np.int32(value)).tobytes(), dtype=np.uint8)
+        bad[:256] = torch.from_numpy(h2).cuda()
+        with pytest.raises(rtb200.RtError, match="rejected|mismatch"):
+            c2.adopt_scene_blob(bad.data_ptr(), nbytes)
+    with pytest.raises(rtb200.RtError):
+        c2.adopt_scene_blob(moved.data_ptr(), nbytes - 256)
     c2.close()
 
 
