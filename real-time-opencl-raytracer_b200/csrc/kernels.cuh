@@ -444,7 +444,7 @@ __global__ void hit_scatter_kernel(long long n, const float4* hits_sorted, const
     if (i < n) out[perm[i]] = hits_sorted[i];
 }
 
-// ---- self test: div_hoisted(x, d, div_prepare(d)) must equal x / d bit for bit over the admitted window ---
+// ---- self test: div_hoisted(x, d, div_prepare(d)) and its packed form must equal x / d bit for bit over the admitted window ---
 // d: any sign, exponent in [-20, 20]; x: 0 or any sign, exponent in [-100, 61]; mantissas random or edge patterns.
 // Range probe: same comparison with the numerator's exponent fixed to `ex` (unbiased) and the divisor's exponent
 // in [-20, 20]; used to establish how far below 1.0 the numerator may go before the hoisted sequence (which has no
@@ -466,8 +466,14 @@ __global__ void selftest_division_range_kernel(unsigned int seed, int iters, int
         if (ex >= -126) x = __uint_as_float(((b >> 31) << 31) | ((unsigned int)(ex + 127) << 23) | (b & 0x7FFFFFu));
         else x = __uint_as_float(((b >> 31) << 31) | ((b & 0x7FFFFFu) >> (-126 - ex)));  // denormal with top bit at 2^ex
         const float want = x / d;
-        const float got = div_hoisted(x, d, div_prepare(d));
+        const float r1 = div_prepare(d);
+        const float got = div_hoisted(x, d, r1);
         if (__float_as_uint(want) != __float_as_uint(got) && !(want == 0.0f && got == 0.0f)) bad++;
+        // the packed form the traversal kernels execute (FMUL2 + 2 FFMA2): both halves, numerators x and -x
+        float g0, g1;
+        unpack2(div_hoisted2_core(pack2(x, -x), pack2(-d, -d), pack2(r1, r1)), g0, g1);
+        if (__float_as_uint(want) != __float_as_uint(g0) && !(want == 0.0f && g0 == 0.0f)) bad++;
+        if (__float_as_uint(-want) != __float_as_uint(g1) && !(want == 0.0f && g1 == 0.0f)) bad++;
     }
     if (bad) atomicAdd(mismatches, bad);
 }
@@ -494,8 +500,14 @@ __global__ void selftest_division_kernel(unsigned int seed, int iters, unsigned 
         if ((c >> 24) == 0u) x = 0.0f;
         if (fabsf(d) > 1048576.0f) continue;  // exponent 20 with a non-zero mantissa is outside the window
         const float want = x / d;
-        const float got = div_hoisted(x, d, div_prepare(d));
+        const float r1 = div_prepare(d);
+        const float got = div_hoisted(x, d, r1);
         if (__float_as_uint(want) != __float_as_uint(got) && !(want == 0.0f && got == 0.0f)) bad++;
+        // the packed form the traversal kernels execute (FMUL2 + 2 FFMA2): both halves, numerators x and -x
+        float g0, g1;
+        unpack2(div_hoisted2_core(pack2(x, -x), pack2(-d, -d), pack2(r1, r1)), g0, g1);
+        if (__float_as_uint(want) != __float_as_uint(g0) && !(want == 0.0f && g0 == 0.0f)) bad++;
+        if (__float_as_uint(-want) != __float_as_uint(g1) && !(want == 0.0f && g1 == 0.0f)) bad++;
     }
     if (bad) atomicAdd(mismatches, bad);
 }

@@ -34,15 +34,17 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
     // lane state
     bool has_ray = false;
     bool finished = false;  // SRC_QUEUE: this lane's ray ended in the current iteration
-    Ray ray;
-    RayX rx;
+    RayX rx;  // the lane's ray lives in here (ray_of(rx)); a separate Ray would cost 6 more registers per lane
     float tHit = RTB_T_INIT;
     TraceResult res;
     long long out_index = 0;
     int cur = 0, sp = 0;
     int stack[RTB_STACK];
-    ray.ori = ray.dir = mk3(0.f, 0.f, 1.f);
-    rx = ray_prepare(ray, false);
+    {
+        Ray idle;
+        idle.ori = idle.dir = mk3(0.f, 0.f, 1.f);
+        rx = ray_prepare(idle, false);
+    }
     res.idx = -1; res.t = 0.f; res.u = 0.f; res.v = 0.f;
 
     for (;;) {
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
             }
             if (item < total) {
                 bool active = false;
+                Ray ray;
                 tHit = RTB_T_INIT;
                 if (SRC == SRC_BUFFER) {
                     const float4 o = __ldg(a.rays_in + 2 * item), d = __ldg(a.rays_in + 2 * item + 1);
@@ -144,12 +147,13 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                     ray_box_hoisted(rx, q0, q1, t0n, t0f);
                     ray_box_hoisted(rx, q2, q3, t1n, t1f);
                 } else {
+                    const Ray ray = ray_of(rx);
                     ray_box(ray, q0, q1, t0n, t0f);
                     ray_box(ray, q2, q3, t1n, t1f);
                 }
                 const bool hit0 = (t0n <= t0f) && (t0f >= RTB_TMIN) && (t0n <= tHit);
                 const bool hit1 = (t1n <= t1f) && (t1f >= RTB_TMIN) && (t1n <= tHit);
-                int c0 = __float_as_int(q0.w), c1 = __float_as_int(q2.w);
+                int c0 = box_ref(q1), c1 = box_ref(q3);
                 if (hit0 && hit1) {
                     if (t0n > t1n) { const int t = c0; c0 = c1; c1 = t; }
                     if (sp >= RTB_STACK) {  // reference: stack overflow returns -1 and drops the hit (vR.cl:914)
@@ -182,6 +186,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                 done = true;
             } else {
                 const float4* tp = a.scene.tris + 3 * (size_t)(~cur);
+                const Ray ray = ray_of(rx);
                 for (;;) {
                     const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
                     float u, v;
@@ -219,6 +224,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                 if (lane == leader) base = atomicAdd(a.n_shade, (unsigned long long)__popc(pm));
                 base = __shfl_sync(FULL, base, leader);
                 if (push) {
+                    const Ray ray = ray_of(rx);
                     const unsigned long long slot = base + __popc(pm & lt_mask);
                     a.shade_queue[3 * slot] = make_float4(ray.ori.x, ray.ori.y, ray.ori.z, __int_as_float((int)out_index));
                     a.shade_queue[3 * slot + 1] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, tHit);

@@ -9,8 +9,9 @@
 //   [normal_indices][material diffuse float4 x M][tri_to_material]      every section 256-B aligned
 //
 // Node pair (64 B = 4 x float4, one per INNER node of the reference tree, same topology):
-//   q0 = {c0.min.xyz, bits(ref0)}   q1 = {c0.max.xyz, 0}
-//   q2 = {c1.min.xyz, bits(ref1)}   q3 = {c1.max.xyz, 0}
+//   q0 = {c0.min.x, c0.max.x, c0.min.y, c0.max.y}   q1 = {c0.min.z, c0.max.z, bits(ref0), 0}
+//   q2 = {c1.min.x, c1.max.x, c1.min.y, c1.max.y}   q3 = {c1.min.z, c1.max.z, bits(ref1), 0}
+//   (the two planes of an axis are adjacent: one 64-bit operand of the packed fp32 instructions, device_math.cuh)
 //   c0 = the reference node's offset_left child, c1 = offset_right child (order preserved: the
 //   traversal's "left first on ties" rule depends on it).
 //   ref >= 0          : index of the child's own pair (child is an inner node)
@@ -31,7 +32,7 @@
 namespace rtb {
 
 static const uint32_t kBlobMagic = 0x42325452u;  // "RT2B"
-static const uint32_t kBlobVersion = 4;
+static const uint32_t kBlobVersion = 5;
 static const int32_t kRefPoison = (int32_t)0x80000000;
 
 struct BlobHeader {

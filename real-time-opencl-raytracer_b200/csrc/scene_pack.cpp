@@ -159,10 +159,11 @@ int pack_scene(const SceneInputs& in, int top_pairs, uint8_t** out_blob, uint64_
         const RefNode& n = nodes[order[p]];
         const RefNode &c0 = nodes[n.left], &c1 = nodes[n.right];
         float* q = pairs + (size_t)p * 16;
-        q[0] = c0.mn[0]; q[1] = c0.mn[1]; q[2] = c0.mn[2]; q[3] = as_float(child_ref(n.left));
-        q[4] = c0.mx[0]; q[5] = c0.mx[1]; q[6] = c0.mx[2]; q[7] = 0.0f;
-        q[8] = c1.mn[0]; q[9] = c1.mn[1]; q[10] = c1.mn[2]; q[11] = as_float(child_ref(n.right));
-        q[12] = c1.mx[0]; q[13] = c1.mx[1]; q[14] = c1.mx[2]; q[15] = 0.0f;
+        // {min.x, max.x, min.y, max.y} {min.z, max.z, ref, 0} per child: the planes of one axis are adjacent (FFMA2 operands)
+        q[0] = c0.mn[0]; q[1] = c0.mx[0]; q[2] = c0.mn[1]; q[3] = c0.mx[1];
+        q[4] = c0.mn[2]; q[5] = c0.mx[2]; q[6] = as_float(child_ref(n.left)); q[7] = 0.0f;
+        q[8] = c1.mn[0]; q[9] = c1.mx[0]; q[10] = c1.mn[1]; q[11] = c1.mx[1];
+        q[12] = c1.mn[2]; q[13] = c1.mx[2]; q[14] = as_float(child_ref(n.right)); q[15] = 0.0f;
         check(c0.mn); check(c0.mx); check(c1.mn); check(c1.mx);
     }
     h.coords_in_window = in_window ? 1 : 0;

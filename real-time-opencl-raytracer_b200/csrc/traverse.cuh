@@ -82,7 +82,7 @@ __device__ __forceinline__ TraceResult traverse(const SceneView& s, const float4
             }
             const bool hit0 = (t0n <= t0f) && (t0f >= RTB_TMIN) && (t0n <= tHit);
             const bool hit1 = (t1n <= t1f) && (t1f >= RTB_TMIN) && (t1n <= tHit);
-            int c0 = __float_as_int(q0.w), c1 = __float_as_int(q2.w);
+            int c0 = box_ref(q1), c1 = box_ref(q3);
             if (hit0 && hit1) {
                 if (t0n > t1n) { const int t = c0; c0 = c1; c1 = t; }
                 if (sp >= RTB_STACK) { res.idx = -1; res.t = tHit; res.u = res.v = 0.0f; return res; }

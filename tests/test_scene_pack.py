@@ -35,13 +35,13 @@ def walk(h, pairs, tris, o, d, tmax, any_hit):
             while cur >= 0:
                 q = pairs[cur]
                 res = []
-                for base in (0, 8):
-                    t0 = (q[base:base + 3] - o) / d
-                    t1 = (q[base + 4:base + 7] - o) / d
+                for base in (0, 8):  # child box = {min.x, max.x, min.y, max.y} {min.z, max.z, ref, 0}
+                    t0 = (q[[base, base + 2, base + 4]] - o) / d
+                    t1 = (q[[base + 1, base + 3, base + 5]] - o) / d
                     tn = np.fmax(np.fmax(np.fmin(t0[0], t1[0]), np.fmin(t0[1], t1[1])), np.fmin(t0[2], t1[2]))
                     tf = np.fmin(np.fmin(np.fmax(t0[0], t1[0]), np.fmax(t0[1], t1[1])), np.fmax(t0[2], t1[2]))
                     res.append((tn, tf, bool(tn <= tf and tf >= TMIN and tn <= t_hit)))
-                c0, c1 = int(pi[cur, 3]), int(pi[cur, 11])
+                c0, c1 = int(pi[cur, 6]), int(pi[cur, 14])
                 if res[0][2] and res[1][2]:
                     if res[0][0] > res[1][0]:
                         c0, c1 = c1, c0
@@ -96,7 +96,7 @@ def test_blob_layout_matches_reference_arrays(name):
     # every pair holds exactly the two child boxes of one reference inner node, left child first
     want = {tuple(np.concatenate([nodes[ints[i, 8], 0:3], nodes[ints[i, 8], 4:7], nodes[ints[i, 9], 0:3], nodes[ints[i, 9], 4:7]]).view(np.uint32))
             for i in inner}
-    got = {tuple(np.concatenate([p[0:3], p[4:7], p[8:11], p[12:15]]).view(np.uint32)) for p in pairs}
+    got = {tuple(p[[0, 2, 4, 1, 3, 5, 8, 10, 12, 9, 11, 13]].view(np.uint32)) for p in pairs}
     assert got == want
     # triangles: v0 | 3*triId, e1 | last, e2, in tri_indices order
     ti = tris.view(np.int32)
