@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
             if (!queue_open) break;
             continue;
         }
+        const bool warp_hoisted = __all_sync(FULL, !has_ray || rx.fast);
 
         // ---- INNER: node-pair visits in lock step -----------------------------------------------
         for (;;) {
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                 const float4* p = a.scene.pairs + 4 * (size_t)cur;
                 const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
                 float t0n, t0f, t1n, t1f;
-                if (rx.fast) {
+                if (warp_hoisted || rx.fast) {  // warp_hoisted is uniform: no divergent branch in the common case
                     ray_box_hoisted(rx, q0, q1, t0n, t0f);
                     ray_box_hoisted(rx, q2, q3, t1n, t1f);
                 } else {

@@ -43,11 +43,12 @@ struct TraceResult {
 };
 
 // Node fetch policy: TOP > 0 means pairs [0, TOP) are served from shared memory (`smem_pairs`).
-template <bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX = false>
-__device__ __forceinline__ TraceResult traverse(const SceneView& s, const float4* __restrict__ smem_pairs, int smem_count,
-                                                const Ray& ray, float tHit) {
-    static_assert(!(ANY_HIT && FAST_BOX), "the approximate box test is for closest-hit only");
-    const RayX rx = ray_prepare(ray, s.coords_in_window != 0);
+// ALL_HOISTED: every lane that runs this instance has rx.fast set (decided by a warp vote in traverse()), so the
+// per-visit choice between the hoisted and the general box test -- a divergent branch with its reconvergence barrier in
+// the hottest loop -- disappears from the instruction stream.
+template <bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX, bool ALL_HOISTED>
+__device__ __forceinline__ TraceResult traverse_impl(const SceneView& s, const float4* __restrict__ smem_pairs, int smem_count,
+                                                     const Ray& ray, const RayX& rx, float tHit) {
     RayF rf;
     if (FAST_BOX) rf = ray_fast_prepare(ray);
     int stack[RTB_STACK];
@@ -73,7 +74,7 @@ __device__ __forceinline__ TraceResult traverse(const SceneView& s, const float4
             if (FAST_BOX) {
                 ray_box_fast(ray, rf, q0, q1, t0n, t0f);
                 ray_box_fast(ray, rf, q2, q3, t1n, t1f);
-            } else if (rx.fast) {
+            } else if (ALL_HOISTED || rx.fast) {
                 ray_box_hoisted(rx, q0, q1, t0n, t0f);
                 ray_box_hoisted(rx, q2, q3, t1n, t1f);
             } else {
@@ -119,6 +120,18 @@ __device__ __forceinline__ TraceResult traverse(const SceneView& s, const float4
         if (sp == 0) { res.t = tHit; return res; }
         cur = stack[--sp];
     }
+}
+
+template <bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX = false>
+__device__ __forceinline__ TraceResult traverse(const SceneView& s, const float4* __restrict__ smem_pairs, int smem_count,
+                                                const Ray& ray, float tHit) {
+    static_assert(!(ANY_HIT && FAST_BOX), "the approximate box test is for closest-hit only");
+    const RayX rx = ray_prepare(ray, s.coords_in_window != 0);
+    if (FAST_BOX) return traverse_impl<ANY_HIT, SMEM_TOP, true, false>(s, smem_pairs, smem_count, ray, rx, tHit);
+    // the lanes that traverse together agree (almost always: the scene flag is uniform and directions / origins outside
+    // the window are rare) on the hoisted division; a single lane outside the window sends its warp to the general loop
+    if (__all_sync(__activemask(), rx.fast)) return traverse_impl<ANY_HIT, SMEM_TOP, false, true>(s, smem_pairs, smem_count, ray, rx, tHit);
+    return traverse_impl<ANY_HIT, SMEM_TOP, false, false>(s, smem_pairs, smem_count, ray, rx, tHit);
 }
 
 }  // namespace rtb
