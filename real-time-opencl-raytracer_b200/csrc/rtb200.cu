@@ -67,7 +67,7 @@ struct rt_context {
                                 // -1 = auto: batch for in-kernel camera/shadow rays (coherent), lanes for ray buffers
     int opt_refill = 16;         // persistent lanes: refill when this many lanes are empty
     int opt_inner_exit = 8;     // persistent lanes: leave the inner phase when fewer lanes than this still descend
-    int opt_frame_mode = 1;     // rt_render_frame*: 1 = wavefront pipeline (wavefront.cuh), 0 = one-thread-per-pixel megakernel
+    int opt_frame_mode = 0;     // rt_render_frame*: 0 = one-thread-per-pixel megakernel (render_kernel), 1 = wavefront pipeline (wavefront.cuh)
     int opt_wf_lanes = 1;       // wavefront bounce stages: 1 = persistent-lanes trace + dense shade kernel, 0 = fused batch kernel
     int opt_wf_shadow_lanes = 0; // wavefront shadow stages on the persistent-lanes scheduler: 0 = none, 1 = bounces 1-2, 2 = all
     int opt_wf_late_div = 1;    // wavefront: grids of the later (smaller) stages are divided by this

@@ -199,7 +199,7 @@ def test_wavefront_frame_equals_megakernel(ctx, name):
             ctx.synchronize()
             frames.append(img.cpu())
     finally:
-        ctx.set_option("frame_mode", 1)
+        ctx.set_option("frame_mode", 0)
         ctx.set_option("wf_lanes", 1)
     assert torch.equal(frames[0], frames[1]) and torch.equal(frames[0], frames[2])
     ref_img, _ = O.OracleScene(mesh_dict(g), g["ref_nodes"], g["ref_tri_indices"]).render_frame(params, w, h)
