@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
             if (__popc(m) < inner_exit_threshold && __ballot_sync(FULL, has_ray && cur < 0) != 0) break;
             if (inner) {
                 const float4* p = a.scene.pairs + 4 * (size_t)cur;
-                const float4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+                float4 q0, q1, q2, q3;
+                ldg256(p, q0, q1);
+                ldg256(p + 2, q2, q3);
                 float t0n, t0f, t1n, t1f;
                 if (warp_hoisted || rx.fast) {  // warp_hoisted is uniform: no divergent branch in the common case
                     ray_box_hoisted(rx, q0, q1, t0n, t0f);
