@@ -93,7 +93,8 @@ int rt_upload_scene(rt_context* ctx, const float* verts, int V, const int32_t* i
 int rt_scene_blob(rt_context* ctx, void** out_device_ptr, size_t* out_bytes);
 /* Device-to-device copy of the blob into caller-owned device memory (e.g. the NCCL broadcast buffer). */
 int rt_copy_scene_blob(rt_context* ctx, void* dst_device_ptr, size_t bytes);
-/* Adopt a blob that already sits in this device's memory (borrowed: the caller keeps it alive). */
+/* Adopt a blob that already sits in this device's memory (borrowed: the caller keeps it alive). device_ptr must be
+ * 256-byte aligned; the header and every section range are validated before use. */
 int rt_adopt_scene_blob(rt_context* ctx, void* device_ptr, size_t bytes);
 
 /* Host-only twin of the packing step of rt_upload_scene: same validation, same blob (see csrc/scene_blob.h), returned

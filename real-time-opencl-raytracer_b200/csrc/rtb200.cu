@@ -286,6 +286,8 @@ extern "C" int rt_copy_scene_blob(rt_context* ctx, void* dst_device_ptr, size_t 
 
 extern "C" int rt_adopt_scene_blob(rt_context* ctx, void* device_ptr, size_t bytes) {
     if (!ctx || !device_ptr || bytes < sizeof(BlobHeader)) return RT_E_INVALID;
+    if ((uintptr_t)device_ptr & 255u)  // sections are 256-byte aligned relative to the base; the kernels use 32-byte loads
+        return set_err(ctx, RT_E_INVALID, "rt_adopt_scene_blob: the blob must be 256-byte aligned (got %p)", device_ptr);
     CK(ctx, cudaSetDevice(ctx->device));
     BlobHeader h;
     CK(ctx, cudaMemcpyAsync(&h, device_ptr, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));

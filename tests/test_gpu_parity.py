@@ -536,6 +536,10 @@ def test_scene_blob_adopt_roundtrip(ctx):
             c2.adopt_scene_blob(bad.data_ptr(), nbytes)
     with pytest.raises(rtb200.RtError):
         c2.adopt_scene_blob(moved.data_ptr(), nbytes - 256)
+    shifted = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
+    shifted[16:16 + nbytes] = moved
+    with pytest.raises(rtb200.RtError, match="aligned"):
+        c2.adopt_scene_blob(shifted.data_ptr() + 16, nbytes)
     c2.close()
 
 
