@@ -33,7 +33,7 @@ struct rt_context {
     cudaEvent_t out_events[16] = {nullptr};
     cudaEvent_t wf_events[6] = {nullptr};
     // frames in flight (rt_render_frame_begin / _end)
-    struct FrameSlot { cudaEvent_t done = nullptr; bool pending = false; void* d_out = nullptr; size_t d_bytes = 0; uint32_t* host = nullptr; size_t bytes = 0; } slots[RT_FRAME_SLOTS];
+    struct FrameSlot { cudaEvent_t done = nullptr; cudaEvent_t start = nullptr; cudaStream_t stream = nullptr; bool pending = false; void* d_out = nullptr; size_t d_bytes = 0; uint32_t* host = nullptr; size_t bytes = 0; } slots[RT_FRAME_SLOTS];
     void* d_sort = nullptr;               // ray-sorting scratch (keys, permutation, sorted rays, sorted hits, cub temp)
     size_t sort_bytes = 0;
     void* d_wf = nullptr;                 // wavefront scratch: path state + ray queues + counters
@@ -76,6 +76,7 @@ struct rt_context {
     int opt_tile_order = 0;     // primary-ray tile order (see TraceArgs::tile_order)
     int opt_zero_copy = 1;      // rt_primary: store hits directly into pinned host memory when the destination is pinned
     int opt_exact_div = 0;      // 1 = always use the compiler's full division in the box test
+    int opt_overlap_frames = 1; // rt_render_frame_begin: one-kernel frames on per-slot streams (frames in flight overlap)
     uint64_t counters[RT_CNT_COUNT] = {0};
     // resident blocks per SM of each kernel (occupancy query is a slow host call: done once per kernel and smem size)
     struct OccEntry { const void* fn; size_t smem; int per_sm; } occ_cache[32];
@@ -120,7 +121,11 @@ static int init_context(rt_context* ctx, int device_ordinal) {
     for (auto& ev : ctx->chunk_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : ctx->out_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : ctx->wf_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    for (auto& sl : ctx->slots) CK(nullptr, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    for (auto& sl : ctx->slots) {
+        CK(nullptr, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        CK(nullptr, cudaEventCreateWithFlags(&sl.start, cudaEventDisableTiming));
+        CK(nullptr, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    }
     CK(nullptr, cudaMalloc(&ctx->d_counter, 256));
     memset(&ctx->hdr, 0, sizeof ctx->hdr);
     memset(&ctx->view, 0, sizeof ctx->view);
@@ -174,6 +179,8 @@ extern "C" int rt_destroy(rt_context* ctx) {
         if (ev) cudaEventDestroy(ev);
     for (auto& sl : ctx->slots) {
         if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.start) cudaEventDestroy(sl.start);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
         cudaFree(sl.d_out);
     }
     cudaFree(ctx->d_wf);
@@ -320,7 +327,8 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     else if (!strcmp(name, "exact_div")) {
         ctx->opt_exact_div = value ? 1 : 0;
         if (ctx->have_scene) ctx->view.coords_in_window = ctx->opt_exact_div ? 0 : ctx->hdr.coords_in_window;
-    } else if (!strcmp(name, "top_pairs")) ctx->opt_top_pairs = value < 0 ? 0 : value;  // takes effect at the next upload
+    } else if (!strcmp(name, "overlap_frames")) ctx->opt_overlap_frames = value ? 1 : 0;
+    else if (!strcmp(name, "top_pairs")) ctx->opt_top_pairs = value < 0 ? 0 : value;  // takes effect at the next upload
     else return set_err(ctx, RT_E_INVALID, "rt_set_option: unknown option '%s'", name);
     return RT_OK;
 }
@@ -367,7 +375,10 @@ static int blocks_per_sm(rt_context* ctx, K kernel, size_t smem, int* out) {
 }
 
 template <typename K>
-static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, int smem_count) {
+static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, int smem_count, cudaStream_t stream = nullptr,
+                             unsigned long long* counter = nullptr) {
+    if (!stream) stream = ctx->stream;
+    if (!counter) counter = ctx->d_counter;
     const size_t smem = (size_t)smem_count * 64;
     int per_sm = ctx->opt_blocks_per_sm;
     {
@@ -379,9 +390,9 @@ static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, int smem_c
     const long long needed = (a.num_batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > needed) blocks = needed;
     if (blocks < 1) return RT_OK;  // nothing to do
-    a.work_counter = ctx->d_counter;
-    CK(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
-    kernel<<<(unsigned)blocks, kBlockThreads, smem, ctx->stream>>>(a, smem_count);
+    a.work_counter = counter;
+    CK(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    kernel<<<(unsigned)blocks, kBlockThreads, smem, stream>>>(a, smem_count);
     CK(ctx, cudaGetLastError());
     ctx->counters[RT_CNT_KERNEL_LAUNCHES]++;
     return RT_OK;
@@ -885,7 +896,9 @@ static int render_wavefront(rt_context* ctx, const TraceArgs& ta, uint32_t* d_ou
     return RT_OK;
 }
 
-extern "C" int rt_render_frame_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, uint32_t* d_out) {
+// `stream` / `counter` non-null: the one-kernel frame on a stream of its own (frames in flight overlap on the GPU)
+static int render_frame_impl(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, uint32_t* d_out,
+                             cudaStream_t stream, unsigned long long* counter) {
     int rc = require(ctx, true, true);
     if (rc) return rc;
     if (!d_out) return set_err(ctx, RT_E_INVALID, "rt_render_frame_device: d_out is NULL");
@@ -906,8 +919,12 @@ extern "C" int rt_render_frame_device(rt_context* ctx, int w, int h, int part, i
     if ((rc = band_setup(ctx, a, w, h, part, n_parts, band_rows))) return rc;
     a.frame_out = d_out;
     const int st = smem_top_count(ctx);
-    rc = st ? launch_persistent(ctx, render_kernel<true>, a, st) : launch_persistent(ctx, render_kernel<false>, a, 0);
+    rc = st ? launch_persistent(ctx, render_kernel<true>, a, st, stream, counter) : launch_persistent(ctx, render_kernel<false>, a, 0, stream, counter);
     return rc;
+}
+
+extern "C" int rt_render_frame_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, uint32_t* d_out) {
+    return render_frame_impl(ctx, w, h, part, n_parts, band_rows, d_out, nullptr, nullptr);
 }
 
 extern "C" int rt_render_frame(rt_context* ctx, int w, int h, uint32_t* out_host) {
@@ -941,17 +958,27 @@ extern "C" int rt_render_frame_begin(rt_context* ctx, int w, int h, uint32_t* ou
     if (sl.pending) return set_err(ctx, RT_E_INVALID, "rt_render_frame_begin: slot %d still has a frame in flight (call rt_render_frame_end first)", slot);
     CK(ctx, cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)w * h * 4;
+    // One-kernel frames run on the slot's own stream with the slot's own work counter, ordered after everything already
+    // enqueued on the context stream: the ramp-down of frame k (12-19 % of a launch) overlaps the start of frame k+1.
+    // The wavefront pipeline shares its scratch between frames and stays on the context stream.
+    const bool own = ctx->opt_frame_mode == 0 && ctx->opt_overlap_frames;
+    cudaStream_t stream = own ? sl.stream : nullptr;
+    unsigned long long* counter = own ? ctx->d_counter + 1 + slot : nullptr;
+    if (own) {
+        CK(ctx, cudaEventRecord(sl.start, ctx->stream));
+        CK(ctx, cudaStreamWaitEvent(sl.stream, sl.start, 0));
+    }
     void* alias = ctx->opt_zero_copy ? pinned_alias(out_host) : nullptr;
     if (alias) {
-        if ((rc = rt_render_frame_device(ctx, w, h, 0, 1, 4, (uint32_t*)alias))) return rc;
+        if ((rc = render_frame_impl(ctx, w, h, 0, 1, 4, (uint32_t*)alias, stream, counter))) return rc;
         sl.host = nullptr;
     } else {  // pageable destination: per-slot device frame, copied out by rt_render_frame_end
         if ((rc = ensure(ctx, &sl.d_out, &sl.d_bytes, bytes))) return rc;
-        if ((rc = rt_render_frame_device(ctx, w, h, 0, 1, 4, (uint32_t*)sl.d_out))) return rc;
+        if ((rc = render_frame_impl(ctx, w, h, 0, 1, 4, (uint32_t*)sl.d_out, stream, counter))) return rc;
         sl.host = out_host;
     }
     sl.bytes = bytes;
-    CK(ctx, cudaEventRecord(sl.done, ctx->stream));
+    CK(ctx, cudaEventRecord(sl.done, own ? sl.stream : ctx->stream));
     sl.pending = true;
     return RT_OK;
 }
