@@ -597,14 +597,16 @@ def test_full_size_properties(ctx):
     assert np.all((h3["idx"] != hits["idx"][sel]) | (h3["t"] < hits["t"][sel]))
 
 
+@pytest.mark.parametrize("frame_mode", [0, 1])
 @pytest.mark.parametrize("pinned", [True, False])
-def test_pipelined_frames_equal_frame_by_frame(ctx, pinned):
+def test_pipelined_frames_equal_frame_by_frame(ctx, pinned, frame_mode):
     """rt_render_frame_begin/_end with several frames in flight (each with its own Params block, set while earlier
     frames are still running) deliver exactly the frames rt_render_frame delivers one by one"""
     import torch
 
     g = load_scene("mix")
     _upload(ctx, g)
+    ctx.set_option("frame_mode", frame_mode)  # 0: one kernel per frame on per-slot streams; 1: wavefront pipeline on the context stream
     w, h = (int(v) for v in g["wh"])
     frames = []
     for k in range(6):  # orbit: rotate a, b, c, campos about the y axis
@@ -634,6 +636,7 @@ def test_pipelined_frames_equal_frame_by_frame(ctx, pinned):
         ctx.render_frame_end(k % slots)
         b = bufs[k % slots]
         got[k] = (b.numpy().view(np.uint32) if pinned else b).copy()
+    ctx.set_option("frame_mode", 0)
     for k in range(len(frames)):
         assert np.array_equal(got[k], want[k]), f"frame {k}"
     ctx.set_params(g["params"])
