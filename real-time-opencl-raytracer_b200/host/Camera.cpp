@@ -13,7 +13,7 @@ Camera::Camera() : center(0.0f, 0.0f, 0.0f), cam_radius(200.0f), cam_alpha(0.0f)
 
 void Camera::add_radius(float dr) {
     cam_radius += dr;
-    update_eye();
+    place_eye();
 }
 
 void Camera::add_rotate(float da, float db) {
@@ -26,18 +26,18 @@ void Camera::add_rotate(float da, float db) {
         cam_beta -= 2.0f * kPi;
     const bool flipped = (cam_beta > kPi / 2.0f) && (cam_beta < 3.0f * kPi / 2.0f);
     up = float3(0.0f, flipped ? -1.0f : 1.0f, 0.0f);
-    update_eye();
+    place_eye();
 }
 
-void Camera::update_eye() {
+void Camera::place_eye() {
     const float cb = cosf(cam_beta), sb = sinf(cam_beta);
     eye.x = center.x + cam_radius * cb * cosf(cam_alpha);
     eye.y = center.y + cam_radius * sb;
     eye.z = center.z + cam_radius * cb * sinf(cam_alpha);
-    update_full();
+    rebuild_basis();
 }
 
-void Camera::update_full() {
+void Camera::rebuild_basis() {
     camera_direction = normalize(center - eye);
     camera_right = normalize(cross(camera_direction, up));
     camera_up = normalize(-cross(camera_direction, camera_right));

@@ -23,6 +23,6 @@ public:
                      const float3& aabb_min, const float3& aabb_max, float out_params[32]) const;
 
 private:
-    void update_eye();
-    void update_full();
+    void place_eye();      // eye from (radius, alpha, beta) around center
+    void rebuild_basis();  // right / up / direction from eye, center, up
 };
