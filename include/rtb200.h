@@ -150,10 +150,27 @@ int rt_primary_device(rt_context* ctx, int w, int h, int part, int n_parts, int 
                       rt_ray* d_rays_out);
 /* Same primary pass with the gather fused into the store: besides (or instead of, d_hits may be NULL) the
  * 16-byte hit records, every pixel's hit index (3 * triangle id or -1) is written to d_idx_frame[y*w+x].
- * d_idx_frame may live on ANOTHER GPU (a peer mapping obtained with rt_ipc_open): each rank then stores its
- * bands straight into rank 0's framebuffer over NVLink and no separate gather collective is needed. */
+ * d_idx_frame may live on ANOTHER GPU (a peer mapping obtained with rt_ipc_open, or cudaDeviceEnablePeerAccess inside
+ * one process): each rank then stores its bands straight into rank 0's framebuffer over NVLink and no separate gather
+ * collective is needed. It may also be page-locked HOST memory (rt_host_register). For such remote frames the kernel
+ * assembles rows: tiles land in a local stage and the last warp of a group of 4 / 16 horizontally adjacent tiles writes
+ * the group's rows as 128- / 512-byte segments (option "store_group": -1 auto, 0 off, 2, 4). */
 int rt_primary_gather_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
                              int32_t* d_idx_frame);
+/* Primary + shadow in ONE launch (BASELINE configs 3 and 5): per pixel the camera ray, the closest hit (first traverse_bvh
+ * call, vR.cl:1238) and, for every hit, the any-hit shadow ray towards the light built exactly as vR.cl:1314,1407-1441.
+ * One launch pays one ramp-down and one fixed cost where rt_primary_device + rt_shadow_device pay two. Outputs, each
+ * optional (NULL): d_hits = the closest-hit records; d_shadow_hits = the shadow rays' any-hit records (idx = -1,
+ * t = RT_T_INIT where the pixel has no hit); d_vis_frame = one 4-byte word per pixel,
+ *     vis = -1 (no hit)   or   3 * triangle id + (occluded ? 1 : 0),
+ * with the reference's rule occluded = shadow idx >= 0 && shadow t > 0.025 (vR.cl:1444-1449). 3 * triangle id is a
+ * multiple of 3, so vis / 3 * 3 is the hit index and vis % 3 the shadow bit. Band arguments as rt_primary_device;
+ * d_vis_frame may be peer or page-locked host memory like d_idx_frame of rt_primary_gather_device. */
+int rt_primary_shadow_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
+                             rt_hit* d_shadow_hits, int32_t* d_vis_frame);
+/* Host-buffer form of the same pass: vis_host receives w*h visibility words (page-locked memory is written by the kernel
+ * directly, in full 128/512-byte rows; pageable memory through a device frame and one copy). */
+int rt_primary_shadow(rt_context* ctx, int w, int h, int32_t* vis_host);
 /* Peer-visible device buffer across processes of one node (CUDA IPC): the owner allocates and passes the
  * 64-byte handle to its peers (any transport), they map it. */
 int rt_ipc_alloc(rt_context* ctx, size_t bytes, void** out_device_ptr, unsigned char out_handle[64]);
@@ -166,6 +183,10 @@ int rt_memcpy_to_host(rt_context* ctx, void* dst_host, const void* src_device, s
  * memory over its OWN PCIe link (the gather needs neither NVLink nor a device->host copy on rank 0). */
 int rt_host_register(rt_context* ctx, void* host_ptr, size_t bytes, void** out_device_alias);
 int rt_host_unregister(rt_context* ctx, void* host_ptr);
+/* Stream-ordered completion signal: after everything enqueued on the context so far has finished (and its stores are
+ * visible system-wide), the 32-bit word at d_word (a device alias from rt_host_register, or device memory) is set to
+ * `value`. Lets the consumer of a multi-GPU frame poll one word per rank instead of joining a barrier every frame. */
+int rt_signal(rt_context* ctx, void* d_word, uint32_t value);
 /* Shadow rays built in-kernel from rays + their closest hits exactly as vR.cl:1314,1407-1441 and
  * traced any-hit. Entries whose hit idx < 0 produce idx = -1, t = RT_T_INIT. d_shadow_rays_out may
  * be NULL. */
@@ -180,7 +201,50 @@ int rt_diffuse_rays_device(rt_context* ctx, int64_t n, const rt_ray* d_rays, con
 /* Frame into a device framebuffer (w*h uint32); band partition as in rt_primary_device. */
 int rt_render_frame_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, uint32_t* d_out);
 
+/* ---- multi-GPU group: one process, N GPUs of one box ------------------------------------------------
+ * The reference drives one device (RayTracer.cpp:2128-2131 takes devices[0]; raytrace_gpgpu, :330-344, enqueues on one
+ * queue). A group is N contexts behind the same seam: the scene is packed and uploaded once and its blob is broadcast
+ * to the other GPUs with ncclBroadcast over NVLink (ncclCommInitAll; NCCL is bound at run time); a frame is split in
+ * interleaved bands of `band_rows` rows (default 16, group option "band_rows"), every GPU traces its bands -- launches are
+ * issued by one worker thread per GPU -- and stores its pixels straight into the caller's frame: page-locked host memory
+ * is written by all GPUs at once, each over its own PCIe link; a pageable frame is gathered in a frame on GPU 0 that
+ * the other GPUs write over NVLink (peer access) and copied out once. The calls return when the frame is complete,
+ * like raytrace_gpgpu(). Frames are bit-identical to the single-context calls. */
+typedef struct rt_group rt_group;
+#define RT_GROUP_MAX_GPUS 16
+enum {
+    RT_GROUP_STAT_BROADCAST_MS = 0, /* device time of the last scene broadcast (CUDA events on GPU 0's stream) */
+    RT_GROUP_STAT_COMM_INIT_MS = 1, /* one-off ncclCommInitAll wall time */
+    RT_GROUP_STAT_BLOB_BYTES = 2,
+    RT_GROUP_STAT_LAST_CALL_MS = 3, /* wall time of the last tiled call */
+    RT_GROUP_STAT_ZERO_COPY = 4,    /* 1 if the last tiled call stored straight into the caller's (page-locked) frame */
+    RT_GROUP_STAT_RANK_KERNEL_MS = 8, /* [8 + rank]: device time of that GPU's part of the last tiled call */
+    RT_GROUP_STATS = 8 + RT_GROUP_MAX_GPUS
+};
+int rt_create_group(int n_gpus, const int* device_ordinals /* NULL = 0..n-1 */, rt_group** out_group);
+int rt_destroy_group(rt_group* g);
+const char* rt_group_last_error(const rt_group* g); /* g may be NULL: last rt_create_group error */
+int rt_group_size(const rt_group* g);
+rt_context* rt_group_context(rt_group* g, int rank); /* borrowed; e.g. for rt_get_counters */
+/* rt_upload_scene on GPU 0 + broadcast of the packed blob + rt_adopt_scene_blob on the others. */
+int rt_group_upload_scene(rt_group* g, const float* verts, int V, const int32_t* indices, int T, const void* nodes, int N,
+                          const int32_t* tri_indices, int R, const float* normals, int Vn, const int32_t* normal_indices,
+                          const void* materials, int M, const int32_t* tri_to_material);
+int rt_group_set_params(rt_group* g, const float params[32]);
+/* "band_rows" (multiple of 4), "broadcast" (0 = ncclBroadcast, 1 = peer copies from GPU 0); any other name is forwarded
+ * to rt_set_option of every context. */
+int rt_group_set_option(rt_group* g, const char* name, int value);
+/* rt_render_frame over the group: replaces raytrace_gpgpu() (RayTracer.cpp:330-344) for N GPUs. */
+int rt_render_frame_tiled(rt_group* g, int w, int h, uint32_t* out_host);
+/* The 4-byte/pixel primary pass over the group: with_shadow = 0 -> hit-index frame (rt_primary_gather_device),
+ * with_shadow = 1 -> visibility frame of the fused primary + shadow pass (rt_primary_shadow_device). */
+int rt_primary_tiled(rt_group* g, int w, int h, int with_shadow, int32_t* frame_host);
+int rt_group_stats(rt_group* g, double out[RT_GROUP_STATS]);
+
 /* ---- introspection -------------------------------------------------------------------------- */
+/* RT_CNT_RAYS_TRACED = traversals started (one per traverse_bvh call of the reference: primary rays that pass the scene
+ * gate, shadow rays, reflection rays, caller rays), counted by the kernels themselves; rt_get_counters waits for the
+ * work issued so far before it reads the count. */
 enum { RT_CNT_KERNEL_LAUNCHES = 0, RT_CNT_RAYS_TRACED = 1, RT_CNT_H2D_BYTES = 2, RT_CNT_D2H_BYTES = 3, RT_CNT_COUNT = 8 };
 int rt_get_counters(rt_context* ctx, uint64_t out[RT_CNT_COUNT]);
 int rt_reset_counters(rt_context* ctx);

@@ -7,5 +7,5 @@ intersection) of itmanager85/real-time-opencl-raytracer behind a C ABI (include/
 
 The directory name contains hyphens, so import it through the `rtb200` shim at the repo root."""
 from . import device, hostlib, tiling  # noqa: F401
-from .device import ANY, CLOSEST, HIT_DTYPE, RAY_DTYPE, T_INIT, Context, RtError, pack_scene_host  # noqa: F401
+from .device import ANY, CLOSEST, HIT_DTYPE, RAY_DTYPE, T_INIT, Context, Group, RtError, pack_scene_host  # noqa: F401
 from .hostlib import FlatBVH, Mesh, camera_params  # noqa: F401

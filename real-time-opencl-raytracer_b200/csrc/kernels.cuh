@@ -16,7 +16,7 @@ struct RayIO {  // rt_ray / rt_hit as two / one 16-byte vectors
     float4 d_pad;   // dx dy dz reserved
 };
 
-enum RaySource { SRC_BUFFER = 0, SRC_PRIMARY = 1, SRC_SHADOW = 2, SRC_QUEUE = 3 };
+enum RaySource { SRC_BUFFER = 0, SRC_PRIMARY = 1, SRC_SHADOW = 2 };
 
 struct TraceArgs {
     SceneView scene;
@@ -34,17 +34,22 @@ struct TraceArgs {
     const float4* rays_in;    // SRC_BUFFER, SRC_SHADOW (2 x float4 per ray)
     const float4* hits_in;    // SRC_SHADOW (closest hits of rays_in)
     float4* hits_out;         // 1 x float4 per ray {bits(idx), t, u, v}
+    float4* shadow_hits_out;  // primary_shadow_kernel only: the any-hit record of each pixel's shadow ray (optional)
     float4* rays_out;         // optional: the generated rays (SRC_PRIMARY, SRC_SHADOW)
-    unsigned int* frame_out;  // render kernel only
-    int* idx_frame_out;       // optional (SRC_PRIMARY): 4-byte/pixel hit-index framebuffer; may be a PEER GPU's memory
-                              // (store-fused gather over NVLink: the pixel goes straight into the gathered frame)
+    // The 4-byte/pixel frame of the pass (optional): the shaded pixel (render_kernel), the hit index (SRC_PRIMARY) or the
+    // visibility word (primary_shadow_kernel). May be memory of ANOTHER GPU (peer mapping: the gather of a multi-GPU frame
+    // is fused into this store) or page-locked host memory (zero copy).
+    unsigned int* frame_out;
     unsigned long long* work_counter;  // persistent-warp work queue head (zeroed before launch)
-    // SRC_QUEUE (wavefront bounce stage): rays {o.xyz, bits(pixel)} {d.xyz, -} whose count lives in device memory;
-    // every ray that hits is appended to the shade queue as {o.xyz, bits(pixel)} {d.xyz, t} {bits(idx), -, -, -}
-    const unsigned long long* n_in_ptr;
-    float4* shade_queue;
-    unsigned long long* n_shade;
-    float* coef_out;          // SRC_QUEUE + ANY_HIT (wavefront shadow stage): coef[pixel] += occluded && t > 0.025 ? 0.25 : 1
+    unsigned long long* ray_counter;   // += traversals started (traverse() calls) by this launch; one atomicAdd per warp at exit
+    // Row assembly for frame_out in remote (host / peer) memory. A warp's 8x4 tile is four 32-byte row pieces; PCIe and
+    // NVLink want full 128-byte writes. With group_log2 > 0 the tiles store into `stage` (a frame-shaped scratch in local
+    // memory, L2-resident) and the LAST warp to finish a group of 2^group_log2 horizontally adjacent tiles copies the
+    // group's four rows to frame_out as 128-byte (4 tiles) or 512-byte (16 tiles) row segments.
+    unsigned int* stage;
+    unsigned int* group_count;  // one arrival counter per (tile row of this rank, group), zeroed before launch
+    int group_log2;             // 0 = off, 2 = 4 tiles (32 px), 4 = 16 tiles (128 px)
+    int groups_x;
 };
 
 #ifndef RTB_MINB_BATCH
@@ -102,8 +107,9 @@ __device__ __forceinline__ Ray shadow_ray(f3 light_pos, const Ray& r, float t, f
     return ray_init(add3(hitpoint, scale3(L, 0.001f)), L);
 }
 
-// Map a primary-ray batch (one warp = one 8x4 pixel tile) to pixel coordinates.
-__device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, int lane, int& x, int& y) {
+// Map a primary-ray batch (one warp = one 8x4 pixel tile) to pixel coordinates. tx = tile column, k = index of the tile row
+// among this rank's tile rows (what the row-assembly counters are indexed by).
+__device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, int lane, int& x, int& y, int& tx, long long& k) {
     if (a.tile_order == 1) batch = a.num_batches - 1 - batch;
     else if (a.tile_order == 2) batch = (long long)(((unsigned long long)batch * a.order_mul) % (unsigned long long)a.num_batches);
     else if (a.tile_order == 3) {
@@ -111,12 +117,60 @@ __device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, 
         const long long c = batch >> 6;
         if (c < chunks) batch = (long long)(((unsigned long long)c * a.order_mul) % (unsigned long long)chunks) * 64 + (batch & 63);
     }
-    const int tx = (int)(batch % a.tiles_x);
-    const long long k = batch / a.tiles_x;  // index among this rank's tile rows
+    tx = (int)(batch % a.tiles_x);
+    k = batch / a.tiles_x;  // index among this rank's tile rows
     const long long band = (long long)a.part + (k / a.band_tile_rows) * a.n_parts;
     const long long tile_row = band * a.band_tile_rows + (k % a.band_tile_rows);
     x = tx * 8 + (lane & 7);
     y = (int)(tile_row * 4 + (lane >> 3));
+}
+__device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, int lane, int& x, int& y) {
+    int tx;
+    long long k;
+    tile_pixel(a, batch, lane, x, y, tx, k);
+}
+
+// RT_CNT_RAYS_TRACED: every lane counts the traversals it starts; one warp reduction + atomicAdd when the warp retires.
+__device__ __forceinline__ void retire_ray_count(const TraceArgs& a, unsigned int traced, int lane) {
+    traced = __reduce_add_sync(0xffffffffu, traced);
+    if (lane == 0 && traced) atomicAdd(a.ray_counter, (unsigned long long)traced);
+}
+
+// Where a tile's lanes put their 4-byte pixel: the destination itself, or the local stage when rows are assembled.
+__device__ __forceinline__ unsigned int* pixel_sink(const TraceArgs& a) { return a.group_log2 ? a.stage : a.frame_out; }
+
+// Row assembly (see TraceArgs::stage). Called by ALL lanes of a warp after they stored their tile's pixels to the stage.
+// Last-arriver pattern: fence, count the tile in, and the warp that completes the group copies it out. The stage was
+// written by other SMs, so it is read around L1 (ld.global.cg).
+__device__ __forceinline__ void finish_tile(const TraceArgs& a, int tx, long long k, int y0, int lane) {
+    if (!a.group_log2) return;
+    __threadfence();
+    __syncwarp();
+    const int gx = tx >> a.group_log2;
+    const int first_tile = gx << a.group_log2;
+    const int tiles_in_group = min(1 << a.group_log2, a.tiles_x - first_tile);
+    unsigned int arrived = 0;
+    if (lane == 0) arrived = atomicAdd(a.group_count + k * a.groups_x + gx, 1u);
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if ((int)arrived + 1 != tiles_in_group) return;
+    __threadfence();
+    const int x0 = first_tile * 8;
+    const int span = tiles_in_group * 8;  // pixels per row of this group
+    if (a.group_log2 == 4 && (a.w & 3) == 0) {  // 16 tiles: one 512-byte row segment per warp store (16 B per lane)
+        const int c = lane * 4;
+        if (c < span && x0 + c < a.w) {
+            for (int r = 0; r < 4 && y0 + r < a.h; r++) {
+                const size_t at = (size_t)(y0 + r) * a.w + x0 + c;
+                *reinterpret_cast<uint4*>(a.frame_out + at) = __ldcg(reinterpret_cast<const uint4*>(a.stage + at));
+            }
+        }
+    } else {  // 128 bytes per warp store
+        for (int r = 0; r < 4 && y0 + r < a.h; r++) {
+            const size_t row = (size_t)(y0 + r) * a.w;
+            for (int c = lane; c < span; c += 32)
+                if (x0 + c < a.w) a.frame_out[row + x0 + c] = __ldcg(a.stage + row + x0 + c);
+        }
+    }
 }
 
 __device__ __forceinline__ void store_ray(float4* rays_out, long long i, const Ray& r) {
@@ -135,6 +189,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
+    unsigned int traced = 0;
     for (;;) {
         unsigned long long batch = 0;
         if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
@@ -145,6 +200,8 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
         float tmax = RTB_T_INIT;
         long long out_index = -1;
         bool active = false;
+        int tile_x = 0, tile_y0 = 0;
+        long long tile_k = 0;
         if (SRC == SRC_BUFFER) {
             const long long i = (long long)batch * 32 + lane;
             if (i < a.n) {
@@ -157,7 +214,8 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
             }
         } else if (SRC == SRC_PRIMARY) {
             int x, y;
-            tile_pixel(a, (long long)batch, lane, x, y);
+            tile_pixel(a, (long long)batch, lane, x, y, tile_x, tile_k);
+            tile_y0 = y - (lane >> 3);
             if (x < a.w && y < a.h) {
                 out_index = (long long)y * a.w + x;
                 if (a.rays_out || !certainly_gated_out(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h))
@@ -165,7 +223,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
                 if (a.rays_out) store_ray(a.rays_out, out_index, ray);
                 if (!active) {
                     if (a.hits_out) a.hits_out[out_index] = make_float4(__int_as_float(-1), RTB_T_INIT, 0.0f, 0.0f);
-                    if (a.idx_frame_out) a.idx_frame_out[out_index] = -1;
+                    if (a.frame_out) pixel_sink(a)[out_index] = 0xffffffffu;
                 }
             }
         } else {  // SRC_SHADOW
@@ -192,11 +250,59 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
             }
         }
         if (active) {
+            traced++;
             const TraceResult r = traverse<ANY_HIT, SMEM_TOP, FAST_BOX>(a.scene, smem_pairs, smem_count, ray, tmax);
             if (SRC != SRC_PRIMARY || a.hits_out) a.hits_out[out_index] = make_float4(__int_as_float(r.idx), r.t, r.u, r.v);
-            if (SRC == SRC_PRIMARY && a.idx_frame_out) a.idx_frame_out[out_index] = r.idx;
+            if (SRC == SRC_PRIMARY && a.frame_out) pixel_sink(a)[out_index] = (unsigned int)r.idx;
         }
+        if (SRC == SRC_PRIMARY && a.frame_out) finish_tile(a, tile_x, tile_k, tile_y0, lane);
     }
+    retire_ray_count(a, traced, lane);
+}
+
+// ---- primary + shadow in ONE launch (BASELINE config 3 / 5) -------------------------------------------
+// Per pixel: camera ray + scene gate (vR.cl:1156-1196), closest-hit traversal (the first traverse_bvh call, vR.cl:1238),
+// and for every hit the any-hit shadow ray towards the light built exactly as vR.cl:1314,1407-1441. One launch pays one
+// ramp-down and one fixed cost where rt_primary_device + rt_shadow_device pay two -- what limits a frame that is split
+// over 8 GPUs. Outputs (each optional): the closest-hit records, the shadow any-hit records, and the 4-byte/pixel
+// visibility word  vis = -1 (no hit)  |  3*triId + (occluded ? 1 : 0)  with the reference's rule
+// occluded = shadow idx >= 0 && shadow t > 0.025 (vR.cl:1444-1449); 3*triId is a multiple of 3, so the word is lossless.
+__global__ void __launch_bounds__(kBlockThreads) primary_shadow_kernel(const TraceArgs a) {
+    const int lane = threadIdx.x & 31;
+    const f3 light_pos = ld3(a.params.light_pos);
+    unsigned int traced = 0;
+    for (;;) {
+        unsigned long long batch = 0;
+        if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
+        batch = __shfl_sync(0xffffffffu, batch, 0);
+        if (batch >= (unsigned long long)a.num_batches) break;
+        int x, y, tx;
+        long long k;
+        tile_pixel(a, (long long)batch, lane, x, y, tx, k);
+        if (x < a.w && y < a.h) {
+            const long long px = (long long)y * a.w + x;
+            Ray ray;
+            TraceResult hit;
+            hit.idx = -1; hit.t = RTB_T_INIT; hit.u = hit.v = 0.0f;
+            TraceResult sh = hit;
+            if (!certainly_gated_out(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h) &&
+                primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray)) {
+                traced++;
+                hit = traverse<false, false>(a.scene, nullptr, 0, ray, RTB_T_INIT);
+                if (hit.idx >= 0) {
+                    traced++;
+                    f3 hp;
+                    const Ray sray = shadow_ray(light_pos, ray, hit.t, hp);
+                    sh = traverse<true, false>(a.scene, nullptr, 0, sray, RTB_T_INIT);
+                }
+            }
+            if (a.hits_out) a.hits_out[px] = make_float4(__int_as_float(hit.idx), hit.t, hit.u, hit.v);
+            if (a.shadow_hits_out) a.shadow_hits_out[px] = make_float4(__int_as_float(sh.idx), sh.t, sh.u, sh.v);
+            if (a.frame_out) pixel_sink(a)[px] = hit.idx < 0 ? 0xffffffffu : (unsigned int)(hit.idx + ((sh.idx >= 0 && sh.t > 0.025f) ? 1 : 0));
+        }
+        if (a.frame_out) finish_tile(a, tx, k, y - (lane >> 3), lane);
+    }
+    retire_ray_count(a, traced, lane);
 }
 
 // ---- frame megakernel: the whole raytracer_bvh kernel (volumeRender.cl:1043-1547) ------------------
@@ -265,7 +371,7 @@ __device__ __forceinline__ unsigned int rgb_to_int(float r, float g, float b) {
 }
 
 // One path vertex of raytracer_bvh (volumeRender.cl:1306-1403, 1407-1441, 1493-1497): shading of the hit, the shadow
-// ray towards the light and the mirror-reflection ray. Shared by the megakernel and the wavefront kernels.
+// ray towards the light and the mirror-reflection ray.
 struct PathVertex {
     f3 rez_color;
     Ray shadow;
@@ -310,7 +416,7 @@ __device__ __forceinline__ unsigned int resolve_pixel(f3 color, float shadow_coe
 
 template <bool SMEM_TOP>
 __device__ __forceinline__ unsigned int render_pixel(const TraceArgs& a, const float4* smem_pairs, int smem_count, unsigned x,
-                                                     unsigned y) {
+                                                     unsigned y, unsigned int& traced) {
     const SceneView& s = a.scene;
     const f3 light_pos = ld3(a.params.light_pos);
     Ray r;
@@ -321,10 +427,12 @@ __device__ __forceinline__ unsigned int render_pixel(const TraceArgs& a, const f
     float shadow_coef_sum = 0.0f;
 
     while (continue_path && ray_depth < RTB_RAY_TRACE_DEPTH) {
+        traced++;
         const TraceResult hit = traverse<false, SMEM_TOP>(s, smem_pairs, smem_count, r, RTB_T_INIT);
         float shadow_coef = 1.0f;
         if (hit.idx >= 0) {
             ray_depth++;
+            traced++;
             const PathVertex pv = shade_path_vertex(s, light_pos, r, hit.idx, hit.t);
             {
                 const TraceResult sh = traverse<true, SMEM_TOP>(s, smem_pairs, smem_count, pv.shadow, RTB_T_INIT);
@@ -341,23 +449,27 @@ __device__ __forceinline__ unsigned int render_pixel(const TraceArgs& a, const f
 }
 
 template <bool SMEM_TOP>
-__global__ void __launch_bounds__(kBlockThreads) render_kernel(const TraceArgs a, int smem_count) {
+__global__ void __launch_bounds__(kBlockThreads, 8) render_kernel(const TraceArgs a, int smem_count) {
     extern __shared__ float4 smem_pairs[];
     if (SMEM_TOP) {
         for (int i = threadIdx.x; i < smem_count * 4; i += blockDim.x) smem_pairs[i] = a.scene.pairs[i];
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
+    unsigned int traced = 0;
     for (;;) {
         unsigned long long batch = 0;
         if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
         batch = __shfl_sync(0xffffffffu, batch, 0);
         if (batch >= (unsigned long long)a.num_batches) break;
-        int x, y;
-        tile_pixel(a, (long long)batch, lane, x, y);
+        int x, y, tx;
+        long long k;
+        tile_pixel(a, (long long)batch, lane, x, y, tx, k);
         if (x < a.w && y < a.h)
-            a.frame_out[(size_t)y * a.w + x] = render_pixel<SMEM_TOP>(a, smem_pairs, smem_count, (unsigned)x, (unsigned)y);
+            pixel_sink(a)[(size_t)y * a.w + x] = render_pixel<SMEM_TOP>(a, smem_pairs, smem_count, (unsigned)x, (unsigned)y, traced);
+        finish_tile(a, tx, k, y - (lane >> 3), lane);
     }
+    retire_ray_count(a, traced, lane);
 }
 
 // ---- synthetic incoherent workload (BASELINE config 4; not part of the reference) -------------------

@@ -24,8 +24,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned long long total = (SRC == SRC_PRIMARY) ? (unsigned long long)a.num_batches * 32ull
-                                     : (SRC == SRC_QUEUE) ? __ldg(a.n_in_ptr) : (unsigned long long)a.n;
+    const unsigned long long total = (SRC == SRC_PRIMARY) ? (unsigned long long)a.num_batches * 32ull : (unsigned long long)a.n;
 
     // warp-local slice of the work queue
     unsigned long long q_next = 0, q_end = 0;
@@ -33,7 +32,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
 
     // lane state
     bool has_ray = false;
-    bool finished = false;  // SRC_QUEUE: this lane's ray ended in the current iteration
+    unsigned int traced = 0;
     RayX rx;  // the lane's ray lives in here (ray_of(rx)); a separate Ray would cost 6 more registers per lane
     float tHit = RTB_T_INIT;
     TraceResult res;
@@ -82,12 +81,6 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                     tHit = o.w;
                     out_index = (long long)item;
                     active = true;
-                } else if (SRC == SRC_QUEUE) {
-                    const float4 o = __ldg(a.rays_in + 2 * item), d = __ldg(a.rays_in + 2 * item + 1);
-                    ray.ori = ld3(o);
-                    ray.dir = ld3(d);
-                    out_index = (long long)__float_as_int(o.w);  // the pixel this path belongs to
-                    active = true;
                 } else if (SRC == SRC_PRIMARY) {
                     int x, y;
                     tile_pixel(a, (long long)(item >> 5), (int)(item & 31), x, y);
@@ -119,6 +112,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                     }
                 }
                 if (active) {
+                    traced++;
                     rx = ray_prepare(ray, a.scene.coords_in_window != 0);
                     cur = a.scene.root_ref;
                     sp = 0;
@@ -160,8 +154,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                 if (hit0 && hit1) {
                     if (t0n > t1n) { const int t = c0; c0 = c1; c1 = t; }
                     if (sp >= RTB_STACK) {  // reference: stack overflow returns -1 and drops the hit (vR.cl:914)
-                        if (SRC == SRC_QUEUE) { res.idx = -1; finished = true; }
-                        else a.hits_out[out_index] = make_float4(__int_as_float(-1), tHit, 0.0f, 0.0f);
+                        a.hits_out[out_index] = make_float4(__int_as_float(-1), tHit, 0.0f, 0.0f);
                         has_ray = false;
                     } else {
                         stack[sp++] = c1;
@@ -172,8 +165,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                 } else if (hit1) {
                     cur = c1;
                 } else if (sp == 0) {
-                    if (SRC == SRC_QUEUE) finished = true;
-                    else a.hits_out[out_index] = make_float4(__int_as_float(res.idx), tHit, res.u, res.v);
+                    a.hits_out[out_index] = make_float4(__int_as_float(res.idx), tHit, res.u, res.v);
                     has_ray = false;
                 } else {
                     cur = stack[--sp];
@@ -210,34 +202,13 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
                 }
             }
             if (done) {
-                if (SRC == SRC_QUEUE) finished = true;
-                else a.hits_out[out_index] = make_float4(__int_as_float(res.idx), tHit, res.u, res.v);
+                a.hits_out[out_index] = make_float4(__int_as_float(res.idx), tHit, res.u, res.v);
                 has_ray = false;
             }
         }
-        if (SRC == SRC_QUEUE && ANY_HIT) {  // shadow stage: one ray per pixel per stage, stages are stream-ordered
-            if (finished) a.coef_out[out_index] += (res.idx >= 0 && tHit > 0.025f) ? 0.25f : 1.0f;  // vR.cl:1444-1449
-            finished = false;
-        } else if (SRC == SRC_QUEUE) {  // hand every ray that finished with a hit to the shade stage (one atomicAdd per warp)
-            const bool push = finished && res.idx >= 0;
-            const unsigned pm = __ballot_sync(FULL, push);
-            if (pm) {
-                const int leader = __ffs(pm) - 1;
-                unsigned long long base = 0;
-                if (lane == leader) base = atomicAdd(a.n_shade, (unsigned long long)__popc(pm));
-                base = __shfl_sync(FULL, base, leader);
-                if (push) {
-                    const Ray ray = ray_of(rx);
-                    const unsigned long long slot = base + __popc(pm & lt_mask);
-                    a.shade_queue[3 * slot] = make_float4(ray.ori.x, ray.ori.y, ray.ori.z, __int_as_float((int)out_index));
-                    a.shade_queue[3 * slot + 1] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, tHit);
-                    a.shade_queue[3 * slot + 2] = make_float4(__int_as_float(res.idx), 0.f, 0.f, 0.f);
-                }
-            }
-            finished = false;
-        }
         __syncwarp();
     }
+    retire_ray_count(a, traced, lane);
 }
 
 }  // namespace rtb

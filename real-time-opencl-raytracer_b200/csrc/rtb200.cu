@@ -15,12 +15,15 @@
 
 #include "kernels.cuh"
 #include "kernels_lanes.cuh"
-#include "wavefront.cuh"
 #include "scene_blob.h"
 
 using namespace rtb;
 
 static_assert(sizeof(rt_ray) == 32 && sizeof(rt_hit) == 16, "ABI record sizes");
+
+// rt_context::d_counter is 32 x u64: [0] work-queue head of the context stream, [1..RT_FRAME_SLOTS] heads of the frame
+// slots, [8] self-test mismatches, [16] traversals started (RT_CNT_RAYS_TRACED, accumulated by the kernels)
+static const int kRayCounterSlot = 16;
 
 struct rt_context {
     int device = 0;
@@ -31,13 +34,14 @@ struct rt_context {
     cudaEvent_t chunk_events[16] = {nullptr};
     cudaStream_t out_stream = nullptr;    // device->host copies of rt_trace chunks
     cudaEvent_t out_events[16] = {nullptr};
-    cudaEvent_t wf_events[6] = {nullptr};
     // frames in flight (rt_render_frame_begin / _end)
-    struct FrameSlot { cudaEvent_t done = nullptr; cudaEvent_t start = nullptr; cudaStream_t stream = nullptr; bool pending = false; void* d_out = nullptr; size_t d_bytes = 0; uint32_t* host = nullptr; size_t bytes = 0; } slots[RT_FRAME_SLOTS];
+    // Row assembly scratch of one in-flight pass (TraceArgs::stage / group_count): a frame-shaped stage in local memory and
+    // [work-queue head, 256 B][one arrival counter per tile group], zeroed by one memset per launch.
+    struct RowAsm { void* stage = nullptr; size_t stage_bytes = 0; void* counts = nullptr; size_t counts_bytes = 0; };
+    RowAsm rowasm;
+    struct FrameSlot { cudaEvent_t done = nullptr; cudaEvent_t start = nullptr; cudaStream_t stream = nullptr; bool pending = false; void* d_out = nullptr; size_t d_bytes = 0; uint32_t* host = nullptr; size_t bytes = 0; RowAsm rowasm; } slots[RT_FRAME_SLOTS];
     void* d_sort = nullptr;               // ray-sorting scratch (keys, permutation, sorted rays, sorted hits, cub temp)
     size_t sort_bytes = 0;
-    void* d_wf = nullptr;                 // wavefront scratch: path state + ray queues + counters
-    size_t wf_bytes = 0;
     // scene
     uint8_t* d_blob = nullptr;
     size_t blob_bytes = 0;
@@ -67,16 +71,13 @@ struct rt_context {
                                 // -1 = auto: batch for in-kernel camera/shadow rays (coherent), lanes for ray buffers
     int opt_refill = 16;         // persistent lanes: refill when this many lanes are empty
     int opt_inner_exit = 8;     // persistent lanes: leave the inner phase when fewer lanes than this still descend
-    int opt_frame_mode = 0;     // rt_render_frame*: 0 = one-thread-per-pixel megakernel (render_kernel), 1 = wavefront pipeline (wavefront.cuh)
-    int opt_wf_lanes = 1;       // wavefront bounce stages: 1 = persistent-lanes trace + dense shade kernel, 0 = fused batch kernel
-    int opt_wf_shadow_lanes = 0; // wavefront shadow stages on the persistent-lanes scheduler: 0 = none, 1 = bounces 1-2, 2 = all
-    int opt_wf_late_div = 1;    // wavefront: grids of the later (smaller) stages are divided by this
-    int opt_wf_split = 0;       // wavefront: blocks per SM given to the shadow stream when it overlaps a trace stage (0 = full grids)
     int opt_fast_box = 0;       // 1 = approximate reciprocal/FMA box test for CLOSEST-hit batch kernels (NOT bit-exact; experiment)
     int opt_tile_order = 0;     // primary-ray tile order (see TraceArgs::tile_order)
     int opt_zero_copy = 1;      // rt_primary: store hits directly into pinned host memory when the destination is pinned
     int opt_exact_div = 0;      // 1 = always use the compiler's full division in the box test
     int opt_overlap_frames = 1; // rt_render_frame_begin: one-kernel frames on per-slot streams (frames in flight overlap)
+    int opt_store_group = -1;   // row assembly of 4-byte/pixel frames: -1 = auto (on when the frame is host or peer memory),
+                                // 0 = off, 2 = groups of 4 tiles (128-byte rows), 4 = groups of 16 tiles (512-byte rows)
     uint64_t counters[RT_CNT_COUNT] = {0};
     // resident blocks per SM of each kernel (occupancy query is a slow host call: done once per kernel and smem size)
     struct OccEntry { const void* fn; size_t smem; int per_sm; } occ_cache[32];
@@ -84,7 +85,7 @@ struct rt_context {
     std::string err;
 };
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;  // rt_create may run concurrently on several threads (one per GPU)
 
 static int set_err(rt_context* ctx, int code, const char* fmt, ...) {
     char buf[512];
@@ -104,13 +105,32 @@ static int set_err(rt_context* ctx, int code, const char* fmt, ...) {
             return set_err(ctx, RT_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
-extern "C" const char* rt_version(void) { return "rtb200 0.1 (sm_100a)"; }
+// Every entry point runs on its context's device and leaves the calling thread's current device as it found it: a
+// process that also uses another CUDA framework, or drives several contexts from one thread, keeps its own device.
+struct DeviceScope {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceScope(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (prev == device) || cudaSetDevice(device) == cudaSuccess;
+        if (prev == device) prev = -1;  // nothing to restore
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define ON_DEVICE(ctx)                         \
+    DeviceScope device_scope__((ctx)->device); \
+    if (!device_scope__.ok) return set_err(ctx, RT_E_CUDA, "cudaSetDevice(%d) failed", (ctx)->device)
+
+extern "C" const char* rt_version(void) { return "rtb200 0.2 (sm_100a)"; }
 
 extern "C" const char* rt_last_error(const rt_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 static int init_context(rt_context* ctx, int device_ordinal) {
     ctx->device = device_ordinal;
-    CK(nullptr, cudaSetDevice(device_ordinal));
+    DeviceScope scope(device_ordinal);
+    if (!scope.ok) return set_err(nullptr, RT_E_CUDA, "cudaSetDevice(%d) failed", device_ordinal);
     cudaDeviceProp prop;
     CK(nullptr, cudaGetDeviceProperties(&prop, device_ordinal));
     ctx->num_sms = prop.multiProcessorCount;
@@ -120,13 +140,13 @@ static int init_context(rt_context* ctx, int device_ordinal) {
     CK(nullptr, cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
     for (auto& ev : ctx->chunk_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : ctx->out_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    for (auto& ev : ctx->wf_events) CK(nullptr, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& sl : ctx->slots) {
         CK(nullptr, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
         CK(nullptr, cudaEventCreateWithFlags(&sl.start, cudaEventDisableTiming));
         CK(nullptr, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
     }
     CK(nullptr, cudaMalloc(&ctx->d_counter, 256));
+    CK(nullptr, cudaMemset(ctx->d_counter, 0, 256));
     memset(&ctx->hdr, 0, sizeof ctx->hdr);
     memset(&ctx->view, 0, sizeof ctx->view);
     return RT_OK;
@@ -162,7 +182,7 @@ static void free_scene(rt_context* ctx) {
 
 extern "C" int rt_destroy(rt_context* ctx) {
     if (!ctx) return RT_OK;
-    cudaSetDevice(ctx->device);
+    DeviceScope scope(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_scene(ctx);
     cudaFree(ctx->d_counter);
@@ -175,15 +195,16 @@ extern "C" int rt_destroy(rt_context* ctx) {
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->out_events)
         if (ev) cudaEventDestroy(ev);
-    for (auto& ev : ctx->wf_events)
-        if (ev) cudaEventDestroy(ev);
     for (auto& sl : ctx->slots) {
         if (sl.done) cudaEventDestroy(sl.done);
         if (sl.start) cudaEventDestroy(sl.start);
         if (sl.stream) cudaStreamDestroy(sl.stream);
         cudaFree(sl.d_out);
+        cudaFree(sl.rowasm.stage);
+        cudaFree(sl.rowasm.counts);
     }
-    cudaFree(ctx->d_wf);
+    cudaFree(ctx->rowasm.stage);
+    cudaFree(ctx->rowasm.counts);
     cudaFree(ctx->d_sort);
     if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -200,7 +221,7 @@ extern "C" int rt_set_stream(rt_context* ctx, void* cuda_stream) {
 
 extern "C" int rt_synchronize(rt_context* ctx) {
     if (!ctx) return RT_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return RT_OK;
 }
@@ -216,6 +237,7 @@ static const char* header_problem(const BlobHeader& h, size_t bytes) {
         {h.off_mat_diffuse, 16ull * (uint64_t)h.M},          {h.off_tri_to_material, h.M ? 4ull * (uint64_t)h.T : 0ull}};
     for (const auto& s : sec)
         if (s.off < sizeof(BlobHeader) || (s.off & 255u) || s.off > bytes || s.size > bytes - s.off) return "section outside the allocation";
+    if (h.top_pairs > h.num_pairs) return "top_pairs exceeds num_pairs";
     if (h.root_ref >= 0 ? h.root_ref >= h.num_pairs : (h.root_ref != kRefPoison && ~h.root_ref > h.num_tris)) return "root reference out of range";
     return nullptr;
 }
@@ -251,7 +273,7 @@ extern "C" int rt_upload_scene(rt_context* ctx, const float* verts, int V, const
                                int N, const int32_t* tri_indices, int R, const float* normals, int Vn,
                                const int32_t* normal_indices, const void* materials, int M, const int32_t* tri_to_material) {
     if (!ctx) return RT_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     SceneInputs in = {verts, V, indices, T, nodes, N, tri_indices, R, normals, Vn, normal_indices, materials, M, tri_to_material};
     uint8_t* blob = nullptr;
     uint64_t bytes = 0;
@@ -285,7 +307,7 @@ extern "C" int rt_copy_scene_blob(rt_context* ctx, void* dst_device_ptr, size_t 
     if (!ctx || !dst_device_ptr) return RT_E_INVALID;
     if (!ctx->have_scene) return set_err(ctx, RT_E_NO_SCENE, "rt_copy_scene_blob: no scene uploaded");
     if (bytes != ctx->blob_bytes) return set_err(ctx, RT_E_INVALID, "rt_copy_scene_blob: %zu bytes given, blob has %zu", bytes, ctx->blob_bytes);
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     CK(ctx, cudaMemcpyAsync(dst_device_ptr, ctx->d_blob, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return RT_OK;
@@ -295,7 +317,7 @@ extern "C" int rt_adopt_scene_blob(rt_context* ctx, void* device_ptr, size_t byt
     if (!ctx || !device_ptr || bytes < sizeof(BlobHeader)) return RT_E_INVALID;
     if ((uintptr_t)device_ptr & 255u)  // sections are 256-byte aligned relative to the base; the kernels use 32-byte loads
         return set_err(ctx, RT_E_INVALID, "rt_adopt_scene_blob: the blob must be 256-byte aligned (got %p)", device_ptr);
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     BlobHeader h;
     CK(ctx, cudaMemcpyAsync(&h, device_ptr, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -316,11 +338,6 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     else if (!strcmp(name, "scheduler")) ctx->opt_scheduler = value < 0 ? -1 : (value ? 1 : 0);
     else if (!strcmp(name, "refill")) ctx->opt_refill = value < 1 ? 1 : (value > 32 ? 32 : value);
     else if (!strcmp(name, "inner_exit")) ctx->opt_inner_exit = value < 0 ? 0 : (value > 32 ? 32 : value);
-    else if (!strcmp(name, "frame_mode")) ctx->opt_frame_mode = value ? 1 : 0;
-    else if (!strcmp(name, "wf_lanes")) ctx->opt_wf_lanes = value ? 1 : 0;
-    else if (!strcmp(name, "wf_late_div")) ctx->opt_wf_late_div = value < 1 ? 1 : value;
-    else if (!strcmp(name, "wf_shadow_lanes")) ctx->opt_wf_shadow_lanes = value;
-    else if (!strcmp(name, "wf_split")) ctx->opt_wf_split = value < 0 ? 0 : value;
     else if (!strcmp(name, "fast_box")) ctx->opt_fast_box = value ? 1 : 0;
     else if (!strcmp(name, "tile_order")) ctx->opt_tile_order = value < 0 ? 0 : value;
     else if (!strcmp(name, "zero_copy")) ctx->opt_zero_copy = value ? 1 : 0;
@@ -328,6 +345,7 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
         ctx->opt_exact_div = value ? 1 : 0;
         if (ctx->have_scene) ctx->view.coords_in_window = ctx->opt_exact_div ? 0 : ctx->hdr.coords_in_window;
     } else if (!strcmp(name, "overlap_frames")) ctx->opt_overlap_frames = value ? 1 : 0;
+    else if (!strcmp(name, "store_group")) ctx->opt_store_group = (value == 0 || value == 2 || value == 4) ? value : -1;
     else if (!strcmp(name, "top_pairs")) ctx->opt_top_pairs = value < 0 ? 0 : value;  // takes effect at the next upload
     else return set_err(ctx, RT_E_INVALID, "rt_set_option: unknown option '%s'", name);
     return RT_OK;
@@ -347,16 +365,37 @@ extern "C" int rt_scene_info(rt_context* ctx, int64_t out[6]) {
 
 extern "C" int rt_get_counters(rt_context* ctx, uint64_t out[RT_CNT_COUNT]) {
     if (!ctx || !out) return RT_E_INVALID;
+    ON_DEVICE(ctx);
+    // RT_CNT_RAYS_TRACED lives on the device (the kernels count the traversals they start): wait for the work issued so far
+    unsigned long long traced = 0;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& sl : ctx->slots)
+        if (sl.pending) CK(ctx, cudaEventSynchronize(sl.done));
+    CK(ctx, cudaMemcpy(&traced, ctx->d_counter + kRayCounterSlot, sizeof traced, cudaMemcpyDeviceToHost));
+    ctx->counters[RT_CNT_RAYS_TRACED] = traced;
     memcpy(out, ctx->counters, sizeof ctx->counters);
     return RT_OK;
 }
 extern "C" int rt_reset_counters(rt_context* ctx) {
     if (!ctx) return RT_E_INVALID;
+    ON_DEVICE(ctx);
     memset(ctx->counters, 0, sizeof ctx->counters);
+    CK(ctx, cudaMemsetAsync(ctx->d_counter + kRayCounterSlot, 0, sizeof(unsigned long long), ctx->stream));
     return RT_OK;
 }
 
 // ---- launch helpers ------------------------------------------------------------------------------
+
+static int ensure(rt_context* ctx, void** p, size_t* have, size_t need) {
+    if (*have >= need) return RT_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    CK(ctx, cudaMalloc(p, need));
+    *have = need;
+    return RT_OK;
+}
+
 
 template <typename K>
 static int blocks_per_sm(rt_context* ctx, K kernel, size_t smem, int* out) {
@@ -374,12 +413,14 @@ static int blocks_per_sm(rt_context* ctx, K kernel, size_t smem, int* out) {
     return RT_OK;
 }
 
-template <typename K>
-static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, int smem_count, cudaStream_t stream = nullptr,
-                             unsigned long long* counter = nullptr) {
+template <typename K, typename... Extra>
+static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, size_t smem, cudaStream_t stream, unsigned long long* counter,
+                             size_t zero_bytes, Extra... extra) {
     if (!stream) stream = ctx->stream;
-    if (!counter) counter = ctx->d_counter;
-    const size_t smem = (size_t)smem_count * 64;
+    if (!counter) {
+        counter = ctx->d_counter;
+        zero_bytes = sizeof(unsigned long long);
+    }
     int per_sm = ctx->opt_blocks_per_sm;
     {
         int occ = 1, rc = blocks_per_sm(ctx, kernel, smem, &occ);  // also raises the dynamic-smem limit once
@@ -391,10 +432,54 @@ static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, int smem_c
     if (blocks > needed) blocks = needed;
     if (blocks < 1) return RT_OK;  // nothing to do
     a.work_counter = counter;
-    CK(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
-    kernel<<<(unsigned)blocks, kBlockThreads, smem, stream>>>(a, smem_count);
+    a.ray_counter = ctx->d_counter + kRayCounterSlot;
+    CK(ctx, cudaMemsetAsync(counter, 0, zero_bytes, stream));  // queue head (+ the row-assembly arrival counters behind it)
+    kernel<<<(unsigned)blocks, kBlockThreads, smem, stream>>>(a, extra...);
     CK(ctx, cudaGetLastError());
     ctx->counters[RT_CNT_KERNEL_LAUNCHES]++;
+    return RT_OK;
+}
+// trace_kernel / render_kernel take (args, smem_count)
+template <typename K>
+static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, int smem_count, cudaStream_t stream = nullptr,
+                             unsigned long long* counter = nullptr, size_t zero_bytes = sizeof(unsigned long long)) {
+    return launch_persistent(ctx, kernel, a, (size_t)smem_count * 64, stream, counter, zero_bytes, smem_count);
+}
+
+// Destination of a pass's 4-byte/pixel frame. Decides whether rows are assembled (TraceArgs::stage): always when the
+// `store_group` option says so; in auto mode when `dst` is page-locked host memory or memory of another GPU, where a
+// tile's 32-byte row pieces would travel as quarter-filled PCIe / NVLink writes. Local frames are stored directly.
+static int frame_sink(rt_context* ctx, TraceArgs& a, void* dst, rt_context::RowAsm& ra, unsigned long long** counter, size_t* zero_bytes) {
+    a.frame_out = (unsigned int*)dst;
+    a.group_log2 = 0;
+    if (!dst) return RT_OK;
+    int mode = ctx->opt_store_group;
+    if (mode < 0) {
+        cudaPointerAttributes attr;
+        memset(&attr, 0, sizeof attr);
+        mode = 0;
+        if (cudaPointerGetAttributes(&attr, dst) == cudaSuccess) {
+            if (attr.type == cudaMemoryTypeHost) mode = 4;
+            else if (attr.type == cudaMemoryTypeDevice && attr.device != ctx->device) mode = 2;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    if (mode == 4 && (((uintptr_t)dst & 15u) || (a.w & 3))) mode = 2;  // 512-byte rows are stored as 16 bytes per lane
+    if (!mode) return RT_OK;
+    const int group_tiles = 1 << mode;
+    const long long groups_x = (a.tiles_x + group_tiles - 1) / group_tiles;
+    const long long tile_rows = a.tiles_x ? a.num_batches / a.tiles_x : 0;
+    const size_t counts_bytes = 256 + (size_t)(tile_rows * groups_x) * sizeof(unsigned int);
+    int rc;
+    if ((rc = ensure(ctx, &ra.stage, &ra.stage_bytes, (size_t)a.w * a.h * 4))) return rc;
+    if ((rc = ensure(ctx, &ra.counts, &ra.counts_bytes, counts_bytes))) return rc;
+    a.stage = (unsigned int*)ra.stage;
+    a.group_count = (unsigned int*)ra.counts + 64;
+    a.group_log2 = mode;
+    a.groups_x = (int)groups_x;
+    *counter = (unsigned long long*)ra.counts;
+    *zero_bytes = counts_bytes;
     return RT_OK;
 }
 
@@ -410,11 +495,22 @@ static int launch_lanes(rt_context* ctx, K kernel, TraceArgs& a, long long total
     if (blocks > needed) blocks = needed;
     if (blocks < 1) return RT_OK;
     a.work_counter = ctx->d_counter;
+    a.ray_counter = ctx->d_counter + kRayCounterSlot;
     CK(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
     kernel<<<(unsigned)blocks, kBlockThreads, 0, ctx->stream>>>(a, ctx->opt_refill, ctx->opt_inner_exit);
     CK(ctx, cudaGetLastError());
     ctx->counters[RT_CNT_KERNEL_LAUNCHES]++;
     return RT_OK;
+}
+
+// Device alias of a pinned (page-locked) host buffer, or nullptr for pageable memory.
+static void* pinned_alias(const void* host_ptr) {
+    cudaPointerAttributes attr;
+    memset(&attr, 0, sizeof attr);
+    if (cudaPointerGetAttributes(&attr, host_ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        return attr.devicePointer;
+    cudaGetLastError();  // pageable memory is not an error
+    return nullptr;
 }
 
 static int smem_top_count(const rt_context* ctx) {
@@ -478,18 +574,7 @@ static int do_trace_device(rt_context* ctx, int mode, long long n, const rt_ray*
     else
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, true>, a, st)
                 : launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, false>, a, 0);
-    if (rc == RT_OK) ctx->counters[RT_CNT_RAYS_TRACED] += (uint64_t)n;
     return rc;
-}
-
-static int ensure(rt_context* ctx, void** p, size_t* have, size_t need) {
-    if (*have >= need) return RT_OK;
-    if (*p) cudaFree(*p);
-    *p = nullptr;
-    *have = 0;
-    CK(ctx, cudaMalloc(p, need));
-    *have = need;
-    return RT_OK;
 }
 
 // Trace a ray buffer in coherence order: key generation -> radix sort -> gather -> trace -> scatter the hits back to
@@ -499,7 +584,7 @@ extern "C" int rt_trace_sorted_device(rt_context* ctx, int mode, int64_t n, cons
     if (rc) return rc;
     if ((mode != RT_CLOSEST && mode != RT_ANY) || n < 0 || n > 0x7fffffff || (n > 0 && (!d_rays || !d_hits)))
         return set_err(ctx, RT_E_INVALID, "rt_trace_sorted_device: bad arguments");
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (n == 0) return RT_OK;
     const size_t N = (size_t)n, npad = (N + 63) & ~(size_t)63;
     size_t tmp = 0;
@@ -537,21 +622,11 @@ extern "C" int rt_trace_device(rt_context* ctx, int mode, int64_t n, const rt_ra
     if (rc) return rc;
     if ((mode != RT_CLOSEST && mode != RT_ANY) || n < 0 || (n > 0 && (!d_rays || !d_hits)))
         return set_err(ctx, RT_E_INVALID, "rt_trace_device: bad arguments");
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (n == 0) return RT_OK;
     return do_trace_device(ctx, mode, n, d_rays, d_hits);
 }
 
-
-// Device alias of a pinned (page-locked) host buffer, or nullptr for pageable memory.
-static void* pinned_alias(const void* host_ptr) {
-    cudaPointerAttributes attr;
-    memset(&attr, 0, sizeof attr);
-    if (cudaPointerGetAttributes(&attr, host_ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
-        return attr.devicePointer;
-    cudaGetLastError();  // pageable memory is not an error
-    return nullptr;
-}
 
 // Host-buffer batch operator. The batch is cut into chunks: the upload of chunk c+1 (copy stream) overlaps the
 // tracing of chunk c (context stream), and results go either straight into pinned host memory (zero copy) or
@@ -562,7 +637,7 @@ extern "C" int rt_trace(rt_context* ctx, int mode, int64_t n, const rt_ray* rays
     if ((mode != RT_CLOSEST && mode != RT_ANY) || n < 0 || (n > 0 && (!rays_host || !hits_host)))
         return set_err(ctx, RT_E_INVALID, "rt_trace: bad arguments");
     if (n == 0) return RT_OK;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if ((rc = ensure(ctx, &ctx->d_stage_in, &ctx->stage_in_bytes, (size_t)n * sizeof(rt_ray)))) return rc;
     rt_hit* direct_out = ctx->opt_zero_copy ? (rt_hit*)pinned_alias(hits_host) : nullptr;
     if (!direct_out && (rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, (size_t)n * sizeof(rt_hit)))) return rc;
@@ -570,21 +645,40 @@ extern "C" int rt_trace(rt_context* ctx, int mode, int64_t n, const rt_ray* rays
     int chunks = (int)((n + chunk_rays - 1) / chunk_rays);
     if (chunks > 16) chunks = 16;
     const int64_t per = (((n + chunks - 1) / chunks) + 31) & ~(int64_t)31;
+    // rays_host / hits_host are borrowed for the duration of this call only: on a failure part-way through, the copies
+    // already enqueued must have finished before returning
+    auto drain = [&]() {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->out_stream);
+    };
+#define CK_DRAIN(call)                                                                                                      \
+    do {                                                                                                                    \
+        cudaError_t e__ = (call);                                                                                           \
+        if (e__ != cudaSuccess) {                                                                                           \
+            drain();                                                                                                        \
+            return set_err(ctx, RT_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);  \
+        }                                                                                                                   \
+    } while (0)
     for (int c = 0; c < chunks; c++) {
         const int64_t lo = (int64_t)c * per, hi = lo + per < n ? lo + per : n;
         if (lo >= hi) break;
         const rt_ray* d_in = (const rt_ray*)ctx->d_stage_in + lo;
-        CK(ctx, cudaMemcpyAsync((void*)d_in, rays_host + lo, (size_t)(hi - lo) * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->copy_stream));
-        CK(ctx, cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
-        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[c], 0));
+        CK_DRAIN(cudaMemcpyAsync((void*)d_in, rays_host + lo, (size_t)(hi - lo) * sizeof(rt_ray), cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK_DRAIN(cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
+        CK_DRAIN(cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[c], 0));
         rt_hit* d_out = direct_out ? direct_out + lo : (rt_hit*)ctx->d_stage_out + lo;
-        if ((rc = do_trace_device(ctx, mode, hi - lo, d_in, d_out))) return rc;
+        if ((rc = do_trace_device(ctx, mode, hi - lo, d_in, d_out))) {
+            drain();
+            return rc;
+        }
         if (!direct_out) {
-            CK(ctx, cudaEventRecord(ctx->out_events[c], ctx->stream));
-            CK(ctx, cudaStreamWaitEvent(ctx->out_stream, ctx->out_events[c], 0));
-            CK(ctx, cudaMemcpyAsync(hits_host + lo, d_out, (size_t)(hi - lo) * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->out_stream));
+            CK_DRAIN(cudaEventRecord(ctx->out_events[c], ctx->stream));
+            CK_DRAIN(cudaStreamWaitEvent(ctx->out_stream, ctx->out_events[c], 0));
+            CK_DRAIN(cudaMemcpyAsync(hits_host + lo, d_out, (size_t)(hi - lo) * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->out_stream));
         }
     }
+#undef CK_DRAIN
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (!direct_out) CK(ctx, cudaStreamSynchronize(ctx->out_stream));
     ctx->counters[RT_CNT_H2D_BYTES] += (uint64_t)n * sizeof(rt_ray);
@@ -597,7 +691,7 @@ static int primary_impl(rt_context* ctx, int w, int h, int part, int n_parts, in
     int rc = require(ctx, true, false);
     if (rc) return rc;
     if (!d_hits && !d_idx_frame) return set_err(ctx, RT_E_INVALID, "primary pass: no output buffer given");
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     TraceArgs a;
     memset(&a, 0, sizeof a);
     a.scene = ctx->view;
@@ -605,17 +699,65 @@ static int primary_impl(rt_context* ctx, int w, int h, int part, int n_parts, in
     if ((rc = band_setup(ctx, a, w, h, part, n_parts, band_rows))) return rc;
     a.hits_out = (float4*)d_hits;
     a.rays_out = (float4*)d_rays_out;
-    a.idx_frame_out = d_idx_frame;
+    unsigned long long* counter = nullptr;
+    size_t zero_bytes = 0;
+    if ((rc = frame_sink(ctx, a, d_idx_frame, ctx->rowasm, &counter, &zero_bytes))) return rc;
     const int st = smem_top_count(ctx);
     if (ctx->opt_scheduler == 1 && !st && d_hits && !d_idx_frame)
         rc = launch_lanes(ctx, trace_lanes_kernel<SRC_PRIMARY, false>, a, a.num_batches * 32);
     else if (ctx->opt_fast_box && !st)
-        rc = launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false, true>, a, 0);
+        rc = launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false, true>, a, 0, nullptr, counter, zero_bytes);
     else
-        rc = st ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, true>, a, st)
-                : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0);
-    if (rc == RT_OK) ctx->counters[RT_CNT_RAYS_TRACED] += (uint64_t)a.num_batches * 32;
+        rc = st ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, true>, a, st, nullptr, counter, zero_bytes)
+                : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0, nullptr, counter, zero_bytes);
     return rc;
+}
+
+// Primary + shadow in one launch (primary_shadow_kernel).
+static int primary_shadow_impl(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
+                               rt_hit* d_shadow_hits, int32_t* d_vis_frame) {
+    int rc = require(ctx, true, false);
+    if (rc) return rc;
+    if (!d_hits && !d_shadow_hits && !d_vis_frame) return set_err(ctx, RT_E_INVALID, "primary+shadow pass: no output buffer given");
+    ON_DEVICE(ctx);
+    TraceArgs a;
+    memset(&a, 0, sizeof a);
+    a.scene = ctx->view;
+    a.params = ctx->params;
+    if ((rc = band_setup(ctx, a, w, h, part, n_parts, band_rows))) return rc;
+    a.hits_out = (float4*)d_hits;
+    a.shadow_hits_out = (float4*)d_shadow_hits;
+    unsigned long long* counter = nullptr;
+    size_t zero_bytes = 0;
+    if ((rc = frame_sink(ctx, a, d_vis_frame, ctx->rowasm, &counter, &zero_bytes))) return rc;
+    return launch_persistent(ctx, primary_shadow_kernel, a, (size_t)0, nullptr, counter, zero_bytes);
+}
+
+extern "C" int rt_primary_shadow_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
+                                        rt_hit* d_shadow_hits, int32_t* d_vis_frame) {
+    return primary_shadow_impl(ctx, w, h, part, n_parts, band_rows, d_hits, d_shadow_hits, d_vis_frame);
+}
+
+// Host-buffer form: the 4-byte/pixel visibility frame of the fused primary + shadow pass. Page-locked destination: the
+// kernel assembles full rows and stores them straight into host memory; pageable: device frame + one copy.
+extern "C" int rt_primary_shadow(rt_context* ctx, int w, int h, int32_t* vis_host) {
+    int rc = require(ctx, true, false);
+    if (rc) return rc;
+    if (!vis_host || w <= 0 || h <= 0) return set_err(ctx, RT_E_INVALID, "rt_primary_shadow: bad arguments");
+    ON_DEVICE(ctx);
+    const size_t bytes = (size_t)w * h * 4;
+    void* alias = ctx->opt_zero_copy ? pinned_alias(vis_host) : nullptr;
+    if (alias) {
+        if ((rc = primary_shadow_impl(ctx, w, h, 0, 1, 4, nullptr, nullptr, (int32_t*)alias))) return rc;
+    } else {
+        if ((rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, bytes))) return rc;
+        if ((rc = primary_shadow_impl(ctx, w, h, 0, 1, 4, nullptr, nullptr, (int32_t*)ctx->d_stage_out))) return rc;
+        CK(ctx, cudaMemcpyAsync(vis_host, ctx->d_stage_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->counters[RT_CNT_H2D_BYTES] += sizeof(ParamsBlock);
+    ctx->counters[RT_CNT_D2H_BYTES] += bytes;
+    return RT_OK;
 }
 
 extern "C" int rt_primary_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
@@ -633,7 +775,7 @@ extern "C" int rt_primary_gather_device(rt_context* ctx, int w, int h, int part,
 extern "C" int rt_ipc_alloc(rt_context* ctx, size_t bytes, void** out_device_ptr, unsigned char out_handle[64]) {
     if (!ctx || !out_device_ptr || !out_handle || !bytes) return RT_E_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     void* p = nullptr;
     CK(ctx, cudaMalloc(&p, bytes));
     cudaIpcMemHandle_t h;
@@ -648,7 +790,7 @@ extern "C" int rt_ipc_alloc(rt_context* ctx, size_t bytes, void** out_device_ptr
 }
 extern "C" int rt_ipc_open(rt_context* ctx, const unsigned char handle[64], void** out_device_ptr) {
     if (!ctx || !handle || !out_device_ptr) return RT_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
     CK(ctx, cudaIpcOpenMemHandle(out_device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
@@ -656,13 +798,13 @@ extern "C" int rt_ipc_open(rt_context* ctx, const unsigned char handle[64], void
 }
 extern "C" int rt_ipc_close(rt_context* ctx, void* device_ptr) {
     if (!ctx || !device_ptr) return RT_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     CK(ctx, cudaIpcCloseMemHandle(device_ptr));
     return RT_OK;
 }
 extern "C" int rt_ipc_free(rt_context* ctx, void* device_ptr) {
     if (!ctx || !device_ptr) return RT_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     CK(ctx, cudaFree(device_ptr));
     return RT_OK;
 }
@@ -670,7 +812,7 @@ extern "C" int rt_ipc_free(rt_context* ctx, void* device_ptr) {
 // device alias kernels can store into directly (zero copy over this GPU's own PCIe link).
 extern "C" int rt_host_register(rt_context* ctx, void* host_ptr, size_t bytes, void** out_device_alias) {
     if (!ctx || !host_ptr || !bytes || !out_device_alias) return RT_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     CK(ctx, cudaHostRegister(host_ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
     cudaError_t e = cudaHostGetDevicePointer(out_device_alias, host_ptr, 0);
     if (e != cudaSuccess) {
@@ -681,13 +823,26 @@ extern "C" int rt_host_register(rt_context* ctx, void* host_ptr, size_t bytes, v
 }
 extern "C" int rt_host_unregister(rt_context* ctx, void* host_ptr) {
     if (!ctx || !host_ptr) return RT_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     CK(ctx, cudaHostUnregister(host_ptr));
+    return RT_OK;
+}
+// Frame-complete signal for a consumer that polls memory instead of joining a barrier: stream-ordered after the work
+// enqueued so far, one 32-bit word (page-locked host memory registered with rt_host_register, or device memory).
+__global__ void signal_word_kernel(volatile unsigned int* word, unsigned int value) {
+    __threadfence_system();
+    *word = value;
+}
+extern "C" int rt_signal(rt_context* ctx, void* d_word, uint32_t value) {
+    if (!ctx || !d_word || ((uintptr_t)d_word & 3u)) return RT_E_INVALID;
+    ON_DEVICE(ctx);
+    signal_word_kernel<<<1, 1, 0, ctx->stream>>>((volatile unsigned int*)d_word, value);
+    CK(ctx, cudaGetLastError());
     return RT_OK;
 }
 extern "C" int rt_memcpy_to_host(rt_context* ctx, void* dst_host, const void* src_device, size_t bytes) {
     if (!ctx || !dst_host || !src_device) return RT_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     CK(ctx, cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->counters[RT_CNT_D2H_BYTES] += bytes;
@@ -700,7 +855,7 @@ extern "C" int rt_primary(rt_context* ctx, int w, int h, rt_hit* hits_host) {
     int rc = require(ctx, true, false);
     if (rc) return rc;
     if (!hits_host || w <= 0 || h <= 0) return set_err(ctx, RT_E_INVALID, "rt_primary: bad arguments");
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     const size_t bytes = (size_t)w * h * sizeof(rt_hit);
     // Pinned (page-locked) destination: let the kernel store the hit records straight into host memory over
     // PCIe (zero copy) -- the transfer then overlaps the tracing completely and no staging copy exists.
@@ -739,7 +894,7 @@ extern "C" int rt_shadow_device(rt_context* ctx, int64_t n, const rt_ray* d_rays
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_rays || !d_hits || !d_shadow_hits))) return set_err(ctx, RT_E_INVALID, "rt_shadow_device: bad arguments");
     if (n == 0) return RT_OK;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     TraceArgs a;
     memset(&a, 0, sizeof a);
     a.scene = ctx->view;
@@ -756,7 +911,6 @@ extern "C" int rt_shadow_device(rt_context* ctx, int64_t n, const rt_ray* d_rays
     else
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, true>, a, st)
                 : launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, false>, a, 0);
-    if (rc == RT_OK) ctx->counters[RT_CNT_RAYS_TRACED] += (uint64_t)n;
     return rc;
 }
 
@@ -766,7 +920,7 @@ extern "C" int rt_diffuse_rays_device(rt_context* ctx, int64_t n, const rt_ray* 
     if (rc) return rc;
     if (n <= 0 || n > 0x7fffffff || !d_rays || !d_hits || spp < 1 || !d_out_rays)
         return set_err(ctx, RT_E_INVALID, "rt_diffuse_rays_device: bad arguments");
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     if (ctx->flags_count < (size_t)n) {
         cudaFree(ctx->d_flags);
         cudaFree(ctx->d_offsets);
@@ -792,146 +946,36 @@ extern "C" int rt_diffuse_rays_device(rt_context* ctx, int64_t n, const rt_ray* 
     return RT_OK;
 }
 
-// The frame as a wavefront pipeline (wavefront.cuh). Trace stages run on the context stream, the shadow stage of
-// bounce k on a second stream concurrently with the trace stage of bounce k+1.
-static int render_wavefront(rt_context* ctx, const TraceArgs& ta, uint32_t* d_out) {
-    const size_t npix = (size_t)ta.w * ta.h;
-    const size_t npad = (npix + 63) & ~(size_t)63;  // every section stays 256-byte aligned (float4 queues)
-    const size_t off_color = 256, off_coef = off_color + 16 * npad, off_depth = off_coef + 4 * npad, off_q = off_depth + 4 * npad;
-    const size_t need = off_q + (5 * 32 + 48) * npad;  // 2 reflection + 3 shadow queues (32 B/ray) + 1 shade queue (48 B/hit)
-    int rc = ensure(ctx, &ctx->d_wf, &ctx->wf_bytes, need);
-    if (rc) return rc;
-    uint8_t* base = (uint8_t*)ctx->d_wf;
-    unsigned long long* cnt = (unsigned long long*)base;  // [0..5] work-queue heads, [8..9] reflection counts, [11..13] shadow counts
-    WavefrontArgs a;
-    memset(&a, 0, sizeof a);
-    a.scene = ta.scene;
-    a.params = ta.params;
-    a.w = ta.w; a.h = ta.h; a.tiles_x = ta.tiles_x; a.part = ta.part; a.n_parts = ta.n_parts; a.band_tile_rows = ta.band_tile_rows;
-    a.num_batches = ta.num_batches; a.tile_order = ta.tile_order; a.order_mul = ta.order_mul;
-    a.color = (float4*)(base + off_color);
-    a.coef = (float*)(base + off_coef);
-    a.depth = (int*)(base + off_depth);
-    a.frame_out = d_out;
-    float4* refl[2] = {(float4*)(base + off_q), (float4*)(base + off_q + 32 * npad)};
-    float4* shad[3] = {(float4*)(base + off_q + 64 * npad), (float4*)(base + off_q + 96 * npad), (float4*)(base + off_q + 128 * npad)};
-    float4* shade_q = (float4*)(base + off_q + 160 * npad);
-    int occ_trace = 1, occ_bounce = 1, occ_shadow = 1, occ_lanes = 1, occ_shadow_lanes = 1;
-    if ((rc = blocks_per_sm(ctx, trace_lanes_kernel<SRC_QUEUE, false>, 0, &occ_lanes))) return rc;
-    if ((rc = blocks_per_sm(ctx, trace_lanes_kernel<SRC_QUEUE, true>, 0, &occ_shadow_lanes))) return rc;
-    if ((rc = blocks_per_sm(ctx, wf_trace_shade_kernel<true>, 0, &occ_trace))) return rc;
-    if ((rc = blocks_per_sm(ctx, wf_trace_shade_kernel<false>, 0, &occ_bounce))) return rc;
-    if ((rc = blocks_per_sm(ctx, wf_shadow_kernel, 0, &occ_shadow))) return rc;
-    const int split = ctx->opt_wf_split;
-    cudaStream_t s_main = ctx->stream, s_shadow = ctx->out_stream;
-    CK(ctx, cudaMemsetAsync(cnt, 0, 128, s_main));
-    for (int b = 0; b < 3; b++) {
-        WavefrontArgs t = a;
-        t.work_counter = cnt + b;
-        t.rays_in = b ? refl[b - 1] : nullptr;
-        t.n_in = b ? cnt + 8 + (b - 1) : nullptr;
-        t.next_out = b < 2 ? refl[b] : nullptr;
-        t.n_next = b < 2 ? cnt + 8 + b : nullptr;
-        t.shadow_out = shad[b];
-        t.n_shadow = cnt + 11 + b;
-        if (b == 0) {
-            long long blocks = (long long)occ_trace * ctx->num_sms;
-            const long long needed = (a.num_batches + kWarpsPerBlock - 1) / kWarpsPerBlock;
-            if (blocks > needed) blocks = needed;
-            if (blocks < 1) blocks = 1;
-            wf_trace_shade_kernel<true><<<(unsigned)blocks, kBlockThreads, 0, s_main>>>(t);
-        } else if (ctx->opt_wf_lanes) {
-            // trace with the persistent-lanes scheduler; rays that hit go to the shade queue, shaded densely afterwards
-            TraceArgs la;
-            memset(&la, 0, sizeof la);
-            la.scene = a.scene;
-            la.rays_in = t.rays_in;
-            la.n_in_ptr = t.n_in;
-            la.shade_queue = shade_q;
-            la.n_shade = cnt + 14 + (b - 1);
-            la.work_counter = t.work_counter;
-            int per_sm = occ_lanes / (b == 2 ? ctx->opt_wf_late_div : 1);
-            if (per_sm < 1) per_sm = 1;
-            trace_lanes_kernel<SRC_QUEUE, false><<<(unsigned)(per_sm * ctx->num_sms), kBlockThreads, 0, s_main>>>(la, ctx->opt_refill, ctx->opt_inner_exit);
-            CK(ctx, cudaGetLastError());
-            wf_shade_kernel<<<(unsigned)(2 * ctx->num_sms), 256, 0, s_main>>>(t, shade_q, cnt + 14 + (b - 1));
-            ctx->counters[RT_CNT_KERNEL_LAUNCHES] += 1;
-        } else {
-            int per_sm = occ_bounce - (split > 0 && split < occ_bounce ? split : 0);
-            wf_trace_shade_kernel<false><<<(unsigned)(per_sm * ctx->num_sms), kBlockThreads, 0, s_main>>>(t);
-        }
-        CK(ctx, cudaGetLastError());
-        CK(ctx, cudaEventRecord(ctx->wf_events[b], s_main));
-        CK(ctx, cudaStreamWaitEvent(s_shadow, ctx->wf_events[b], 0));
-        WavefrontArgs sh = a;
-        sh.work_counter = cnt + 3 + b;
-        sh.rays_in = shad[b];
-        sh.n_in = cnt + 11 + b;
-        int sh_per_sm = (split > 0 && split < occ_shadow && b < 2) ? split : occ_shadow;
-        if (b > 0) sh_per_sm = sh_per_sm / ctx->opt_wf_late_div > 0 ? sh_per_sm / ctx->opt_wf_late_div : 1;
-        if (ctx->opt_wf_shadow_lanes > (b == 0 ? 1 : 0)) {
-            // the shadow rays of the later bounces end after very different numbers of steps: persistent lanes
-            TraceArgs la;
-            memset(&la, 0, sizeof la);
-            la.scene = a.scene;
-            la.rays_in = sh.rays_in;
-            la.n_in_ptr = sh.n_in;
-            la.coef_out = a.coef;
-            la.work_counter = sh.work_counter;
-            int per_sm = occ_shadow_lanes / (b > 0 ? ctx->opt_wf_late_div : 1);
-            if (per_sm < 1) per_sm = 1;
-            trace_lanes_kernel<SRC_QUEUE, true><<<(unsigned)(per_sm * ctx->num_sms), kBlockThreads, 0, s_shadow>>>(la, ctx->opt_refill, ctx->opt_inner_exit);
-        } else {
-            wf_shadow_kernel<<<(unsigned)(sh_per_sm * ctx->num_sms), kBlockThreads, 0, s_shadow>>>(sh);
-        }
-        CK(ctx, cudaGetLastError());
-        ctx->counters[RT_CNT_KERNEL_LAUNCHES] += 2;
-    }
-    CK(ctx, cudaEventRecord(ctx->wf_events[3], s_shadow));
-    CK(ctx, cudaStreamWaitEvent(s_main, ctx->wf_events[3], 0));
-    const long long threads = a.num_batches * 32;
-    wf_resolve_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s_main>>>(a);
-    CK(ctx, cudaGetLastError());
-    ctx->counters[RT_CNT_KERNEL_LAUNCHES] += 1;
-    return RT_OK;
-}
-
-// `stream` / `counter` non-null: the one-kernel frame on a stream of its own (frames in flight overlap on the GPU)
-static int render_frame_impl(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, uint32_t* d_out,
-                             cudaStream_t stream, unsigned long long* counter) {
+// `slot` >= 0: the frame runs on that frame slot's own stream, work-queue head and row-assembly scratch (frames in flight
+// overlap on the GPU); -1: on the context stream.
+static int render_frame_impl(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, uint32_t* d_out, int slot) {
     int rc = require(ctx, true, true);
     if (rc) return rc;
     if (!d_out) return set_err(ctx, RT_E_INVALID, "rt_render_frame_device: d_out is NULL");
-    CK(ctx, cudaSetDevice(ctx->device));
-    if (ctx->opt_frame_mode == 1 && smem_top_count(ctx) == 0) {
-        TraceArgs ta;
-        memset(&ta, 0, sizeof ta);
-        ta.scene = ctx->view;
-        ta.params = ctx->params;
-        if ((rc = band_setup(ctx, ta, w, h, part, n_parts, band_rows))) return rc;
-        if (ta.num_batches < 1) return RT_OK;
-        return render_wavefront(ctx, ta, d_out);
-    }
+    ON_DEVICE(ctx);
     TraceArgs a;
     memset(&a, 0, sizeof a);
     a.scene = ctx->view;
     a.params = ctx->params;
     if ((rc = band_setup(ctx, a, w, h, part, n_parts, band_rows))) return rc;
-    a.frame_out = d_out;
+    cudaStream_t stream = slot >= 0 ? ctx->slots[slot].stream : nullptr;
+    unsigned long long* counter = slot >= 0 ? ctx->d_counter + 1 + slot : nullptr;
+    size_t zero_bytes = sizeof(unsigned long long);
+    if ((rc = frame_sink(ctx, a, d_out, slot >= 0 ? ctx->slots[slot].rowasm : ctx->rowasm, &counter, &zero_bytes))) return rc;
     const int st = smem_top_count(ctx);
-    rc = st ? launch_persistent(ctx, render_kernel<true>, a, st, stream, counter) : launch_persistent(ctx, render_kernel<false>, a, 0, stream, counter);
-    return rc;
+    return st ? launch_persistent(ctx, render_kernel<true>, a, st, stream, counter, zero_bytes)
+              : launch_persistent(ctx, render_kernel<false>, a, 0, stream, counter, zero_bytes);
 }
 
 extern "C" int rt_render_frame_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, uint32_t* d_out) {
-    return render_frame_impl(ctx, w, h, part, n_parts, band_rows, d_out, nullptr, nullptr);
+    return render_frame_impl(ctx, w, h, part, n_parts, band_rows, d_out, -1);
 }
 
 extern "C" int rt_render_frame(rt_context* ctx, int w, int h, uint32_t* out_host) {
     int rc = require(ctx, true, true);
     if (rc) return rc;
     if (!out_host || w <= 0 || h <= 0) return set_err(ctx, RT_E_INVALID, "rt_render_frame: bad arguments");
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     const size_t bytes = (size_t)w * h * 4;
     void* alias = ctx->opt_zero_copy ? pinned_alias(out_host) : nullptr;
     if (alias) {  // pinned destination: the kernel stores the pixels straight into host memory
@@ -956,25 +1000,22 @@ extern "C" int rt_render_frame_begin(rt_context* ctx, int w, int h, uint32_t* ou
     if (slot < 0 || slot >= RT_FRAME_SLOTS) return set_err(ctx, RT_E_INVALID, "rt_render_frame_begin: slot %d outside 0..%d", slot, RT_FRAME_SLOTS - 1);
     rt_context::FrameSlot& sl = ctx->slots[slot];
     if (sl.pending) return set_err(ctx, RT_E_INVALID, "rt_render_frame_begin: slot %d still has a frame in flight (call rt_render_frame_end first)", slot);
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     const size_t bytes = (size_t)w * h * 4;
-    // One-kernel frames run on the slot's own stream with the slot's own work counter, ordered after everything already
-    // enqueued on the context stream: the ramp-down of frame k (12-19 % of a launch) overlaps the start of frame k+1.
-    // The wavefront pipeline shares its scratch between frames and stays on the context stream.
-    const bool own = ctx->opt_frame_mode == 0 && ctx->opt_overlap_frames;
-    cudaStream_t stream = own ? sl.stream : nullptr;
-    unsigned long long* counter = own ? ctx->d_counter + 1 + slot : nullptr;
+    // Frames run on the slot's own stream with the slot's own work counter, ordered after everything already enqueued on
+    // the context stream: the ramp-down of frame k (12-19 % of a launch) overlaps the start of frame k+1.
+    const bool own = ctx->opt_overlap_frames != 0;
     if (own) {
         CK(ctx, cudaEventRecord(sl.start, ctx->stream));
         CK(ctx, cudaStreamWaitEvent(sl.stream, sl.start, 0));
     }
     void* alias = ctx->opt_zero_copy ? pinned_alias(out_host) : nullptr;
     if (alias) {
-        if ((rc = render_frame_impl(ctx, w, h, 0, 1, 4, (uint32_t*)alias, stream, counter))) return rc;
+        if ((rc = render_frame_impl(ctx, w, h, 0, 1, 4, (uint32_t*)alias, own ? slot : -1))) return rc;
         sl.host = nullptr;
     } else {  // pageable destination: per-slot device frame, copied out by rt_render_frame_end
         if ((rc = ensure(ctx, &sl.d_out, &sl.d_bytes, bytes))) return rc;
-        if ((rc = render_frame_impl(ctx, w, h, 0, 1, 4, (uint32_t*)sl.d_out, stream, counter))) return rc;
+        if ((rc = render_frame_impl(ctx, w, h, 0, 1, 4, (uint32_t*)sl.d_out, own ? slot : -1))) return rc;
         sl.host = out_host;
     }
     sl.bytes = bytes;
@@ -988,10 +1029,10 @@ extern "C" int rt_render_frame_end(rt_context* ctx, int slot) {
     if (slot < 0 || slot >= RT_FRAME_SLOTS) return set_err(ctx, RT_E_INVALID, "rt_render_frame_end: slot %d outside 0..%d", slot, RT_FRAME_SLOTS - 1);
     rt_context::FrameSlot& sl = ctx->slots[slot];
     if (!sl.pending) return set_err(ctx, RT_E_INVALID, "rt_render_frame_end: no frame in flight in slot %d", slot);
-    CK(ctx, cudaSetDevice(ctx->device));
-    sl.pending = false;
-    CK(ctx, cudaEventSynchronize(sl.done));
+    ON_DEVICE(ctx);
+    CK(ctx, cudaEventSynchronize(sl.done));  // on failure the slot stays pending: the caller may retry or destroy the context
     if (sl.host) CK(ctx, cudaMemcpy(sl.host, sl.d_out, sl.bytes, cudaMemcpyDeviceToHost));
+    sl.pending = false;
     ctx->counters[RT_CNT_H2D_BYTES] += sizeof(ParamsBlock);
     ctx->counters[RT_CNT_D2H_BYTES] += sl.bytes;
     return RT_OK;
@@ -1001,7 +1042,7 @@ extern "C" int rt_render_frame_end(rt_context* ctx, int slot) {
 // admitted window, bitwise comparison against the compiler's IEEE division.
 extern "C" int rt_selftest(rt_context* ctx, int64_t samples, uint32_t seed, uint64_t* out_mismatches) {
     if (!ctx || !out_mismatches || samples < 1) return RT_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     CK(ctx, cudaMemsetAsync(ctx->d_counter + 8, 0, sizeof(unsigned long long), ctx->stream));
     const int threads = 256, iters = 4096;
     long long blocks = (samples + (long long)threads * iters - 1) / ((long long)threads * iters);
@@ -1018,7 +1059,7 @@ extern "C" int rt_selftest(rt_context* ctx, int64_t samples, uint32_t seed, uint
 // Range probe of the hoisted division: numerator exponent fixed to `x_exponent` (unbiased, < -126 = denormal).
 extern "C" int rt_selftest_range(rt_context* ctx, int64_t samples, uint32_t seed, int x_exponent, uint64_t* out_mismatches) {
     if (!ctx || !out_mismatches || samples < 1) return RT_E_INVALID;
-    CK(ctx, cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     CK(ctx, cudaMemsetAsync(ctx->d_counter + 8, 0, sizeof(unsigned long long), ctx->stream));
     const int threads = 256, iters = 1024;
     long long blocks = (samples + (long long)threads * iters - 1) / ((long long)threads * iters);

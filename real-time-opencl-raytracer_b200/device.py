@@ -20,8 +20,10 @@ HIT_DTYPE = np.dtype([("idx", np.int32), ("t", np.float32), ("u", np.float32), (
 ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_version", "rt_set_stream", "rt_synchronize", "rt_upload_scene",
     "rt_scene_blob", "rt_copy_scene_blob", "rt_adopt_scene_blob", "rt_set_params", "rt_render_frame", "rt_render_frame_begin", "rt_render_frame_end", "rt_trace", "rt_primary", "rt_trace_device", "rt_trace_sorted_device",
-    "rt_primary_device", "rt_primary_gather_device", "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free",
-    "rt_memcpy_to_host", "rt_host_register", "rt_host_unregister", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
+    "rt_primary_device", "rt_primary_gather_device", "rt_primary_shadow_device", "rt_primary_shadow", "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free",
+    "rt_memcpy_to_host", "rt_host_register", "rt_host_unregister", "rt_signal", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
+    "rt_create_group", "rt_destroy_group", "rt_group_last_error", "rt_group_size", "rt_group_context", "rt_group_upload_scene",
+    "rt_group_set_params", "rt_group_set_option", "rt_render_frame_tiled", "rt_primary_tiled", "rt_group_stats",
     "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest", "rt_selftest_range", "rt_pack_scene_host", "rt_free_host",
 ]
 
@@ -59,6 +61,8 @@ def lib():
         L.rt_primary_device.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
         L.rt_shadow_device.argtypes = [vp, i64, vp, vp, vp, vp]
         L.rt_primary_gather_device.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
+        L.rt_primary_shadow_device.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
+        L.rt_primary_shadow.argtypes = [vp, i32, i32, vp]
         L.rt_ipc_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p]
         L.rt_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
         L.rt_ipc_close.argtypes = [vp, vp]
@@ -66,6 +70,7 @@ def lib():
         L.rt_memcpy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
         L.rt_host_register.argtypes = [vp, vp, C.c_size_t, C.POINTER(vp)]
         L.rt_host_unregister.argtypes = [vp, vp]
+        L.rt_signal.argtypes = [vp, vp, C.c_uint32]
         L.rt_diffuse_rays_device.argtypes = [vp, i64, vp, vp, i32, C.c_uint32, vp, vp]
         L.rt_render_frame_device.argtypes = [vp, i32, i32, i32, i32, i32, vp]
         L.rt_get_counters.argtypes = [vp, vp]
@@ -78,6 +83,19 @@ def lib():
         L.rt_free_host.argtypes = [vp]
         L.rt_free_host.restype = None
         L.rt_selftest_range.argtypes = [vp, i64, C.c_uint32, i32, C.POINTER(C.c_uint64)]
+        L.rt_create_group.argtypes = [i32, vp, C.POINTER(vp)]
+        L.rt_destroy_group.argtypes = [vp]
+        L.rt_group_last_error.argtypes = [vp]
+        L.rt_group_last_error.restype = C.c_char_p
+        L.rt_group_size.argtypes = [vp]
+        L.rt_group_context.argtypes = [vp, i32]
+        L.rt_group_context.restype = vp
+        L.rt_group_upload_scene.argtypes = L.rt_upload_scene.argtypes
+        L.rt_group_set_params.argtypes = [vp, vp]
+        L.rt_group_set_option.argtypes = [vp, C.c_char_p, i32]
+        L.rt_render_frame_tiled.argtypes = [vp, i32, i32, vp]
+        L.rt_primary_tiled.argtypes = [vp, i32, i32, i32, vp]
+        L.rt_group_stats.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -116,6 +134,99 @@ def pack_scene_host(mesh, bvh_nodes, tri_indices, top_pairs=2047, shading=True):
         return np.frombuffer((C.c_char * nbytes.value).from_address(out.value), dtype=np.uint8).copy()
     finally:
         lib().rt_free_host(out)
+
+
+def _scene_args(mesh, bvh_nodes, tri_indices, shading=True):
+    """the 14 scene arguments of rt_upload_scene / rt_group_upload_scene + the arrays that must stay alive during the call"""
+    c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    verts, indices = c(mesh["verts"], np.float32), c(mesh["indices"], np.int32)
+    nodes, tri = c(bvh_nodes, np.float32), c(tri_indices, np.int32)
+    use_shading = shading and len(mesh.get("normals", ())) > 0 and len(mesh.get("materials", ())) > 0
+    if use_shading:
+        normals, nidx = c(mesh["normals"], np.float32), c(mesh["normal_indices"], np.int32)
+        mats, t2m = c(mesh["materials"], np.float32), c(mesh["tri_to_material"], np.int32)
+        Vn, M = normals.shape[0], mats.shape[0]
+    else:
+        normals = nidx = mats = t2m = None
+        Vn = M = 0
+    keep = (verts, indices, nodes, tri, normals, nidx, mats, t2m)
+    return (_ptr(verts), verts.shape[0], _ptr(indices), indices.size // 3, _ptr(nodes), nodes.shape[0], _ptr(tri), tri.size,
+            _ptr(normals), Vn, _ptr(nidx), _ptr(mats), M, _ptr(t2m)), keep
+
+
+class Group:
+    """`rt_group`: one process driving N GPUs of one box (scene broadcast with NCCL, frames split in interleaved row bands,
+    every GPU storing straight into the caller's frame). Mirrors Context for the frame-level calls."""
+
+    STAT_NAMES = {"broadcast_ms": 0, "comm_init_ms": 1, "blob_bytes": 2, "last_call_ms": 3, "zero_copy": 4}
+
+    def __init__(self, n_gpus, devices=None):
+        self._h = C.c_void_p()
+        dev = None
+        if devices is not None:
+            dev = (C.c_int * n_gpus)(*devices)
+        rc = lib().rt_create_group(n_gpus, dev, C.byref(self._h))
+        if rc:
+            raise RtError(f"rt_create_group({n_gpus}) failed [{rc}]: {lib().rt_group_last_error(None).decode()}")
+        self.n = n_gpus
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rt_destroy_group(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise RtError(f"[{rc}] {lib().rt_group_last_error(self._h).decode()}")
+
+    def upload_scene(self, mesh, bvh_nodes, tri_indices, shading=True):
+        args, _keep = _scene_args(mesh, bvh_nodes, tri_indices, shading)
+        self._ck(lib().rt_group_upload_scene(self._h, *args))
+
+    def set_params(self, params32):
+        p = np.ascontiguousarray(params32, dtype=np.float32)
+        assert p.size == 32
+        self._ck(lib().rt_group_set_params(self._h, p.ctypes.data))
+
+    def set_option(self, name, value):
+        self._ck(lib().rt_group_set_option(self._h, name.encode(), int(value)))
+
+    def render_frame(self, w, h, out=None):
+        if out is None:
+            out = np.empty((h, w), dtype=np.uint32)
+        self._ck(lib().rt_render_frame_tiled(self._h, w, h, _ptr(out)))
+        return out
+
+    def primary(self, w, h, with_shadow=False, out=None):
+        """(h, w) int32 frame: hit index (with_shadow=False) or visibility word (True)"""
+        if out is None:
+            out = np.empty((h, w), dtype=np.int32)
+        self._ck(lib().rt_primary_tiled(self._h, w, h, 1 if with_shadow else 0, _ptr(out)))
+        return out
+
+    def stats(self):
+        out = np.zeros(24, dtype=np.float64)
+        self._ck(lib().rt_group_stats(self._h, out.ctypes.data))
+        d = {k: float(out[i]) for k, i in self.STAT_NAMES.items()}
+        d["rank_kernel_ms"] = [float(v) for v in out[8:8 + self.n]]
+        return d
+
+    def rays_traced(self):
+        """sum of RT_CNT_RAYS_TRACED over the group's contexts"""
+        total = 0
+        for r in range(self.n):
+            out = np.zeros(8, dtype=np.uint64)
+            h = lib().rt_group_context(self._h, r)
+            if lib().rt_get_counters(h, out.ctypes.data):
+                raise RtError("rt_get_counters failed")
+            total += int(out[1])
+        return total
 
 
 class Context:
@@ -186,20 +297,8 @@ class Context:
     # --- scene (reference initRayTrace buffers) ---
     def upload_scene(self, mesh, bvh_nodes, tri_indices, shading=True):
         """mesh: dict from hostlib.Mesh.arrays(); bvh_nodes (N,12) f32 words; tri_indices (R,) i32."""
-        c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
-        verts, indices = c(mesh["verts"], np.float32), c(mesh["indices"], np.int32)
-        nodes, tri = c(bvh_nodes, np.float32), c(tri_indices, np.int32)
-        use_shading = shading and len(mesh.get("normals", ())) > 0 and len(mesh.get("materials", ())) > 0
-        if use_shading:
-            normals, nidx = c(mesh["normals"], np.float32), c(mesh["normal_indices"], np.int32)
-            mats, t2m = c(mesh["materials"], np.float32), c(mesh["tri_to_material"], np.int32)
-            Vn, M = normals.shape[0], mats.shape[0]
-        else:
-            normals = nidx = mats = t2m = None
-            Vn = M = 0
-        self._ck(lib().rt_upload_scene(self._h, _ptr(verts), verts.shape[0], _ptr(indices), indices.size // 3, _ptr(nodes),
-                                       nodes.shape[0], _ptr(tri), tri.size, _ptr(normals), Vn, _ptr(nidx), _ptr(mats), M,
-                                       _ptr(t2m)))
+        args, _keep = _scene_args(mesh, bvh_nodes, tri_indices, shading)
+        self._ck(lib().rt_upload_scene(self._h, *args))
 
     def scene_blob(self):
         p, n = C.c_void_p(), C.c_size_t()
@@ -261,6 +360,17 @@ class Context:
         """primary pass that also (or only) stores the 4-byte hit index per pixel into `d_idx_frame` (may be peer memory)"""
         self._ck(lib().rt_primary_gather_device(self._h, w, h, part, n_parts, band_rows, _ptr(d_hits), _ptr(d_idx_frame)))
 
+    def primary_shadow_device(self, w, h, d_hits=None, d_shadow_hits=None, d_vis_frame=None, part=0, n_parts=1, band_rows=4):
+        """primary + any-hit shadow pass in one launch; vis word = -1 | 3*triId + occluded (see include/rtb200.h)"""
+        self._ck(lib().rt_primary_shadow_device(self._h, w, h, part, n_parts, band_rows, _ptr(d_hits), _ptr(d_shadow_hits), _ptr(d_vis_frame)))
+
+    def primary_shadow(self, w, h, vis=None):
+        """host-buffer form: (h, w) int32 visibility frame (numpy array or pinned torch tensor)"""
+        if vis is None:
+            vis = np.empty((h, w), dtype=np.int32)
+        self._ck(lib().rt_primary_shadow(self._h, w, h, _ptr(vis)))
+        return vis
+
     def ipc_alloc(self, nbytes):
         p, handle = C.c_void_p(), C.create_string_buffer(64)
         self._ck(lib().rt_ipc_alloc(self._h, nbytes, C.byref(p), handle))
@@ -285,6 +395,10 @@ class Context:
 
     def host_unregister(self, host_ptr):
         self._ck(lib().rt_host_unregister(self._h, host_ptr))
+
+    def signal(self, d_word, value):
+        """stream-ordered: set the 32-bit word at device-visible address `d_word` once the work enqueued so far is done"""
+        self._ck(lib().rt_signal(self._h, d_word, int(value) & 0xFFFFFFFF))
 
     def memcpy_to_host(self, dst, src_ptr, nbytes):
         self._ck(lib().rt_memcpy_to_host(self._h, _ptr(dst), src_ptr, nbytes))

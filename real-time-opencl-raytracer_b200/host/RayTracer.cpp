@@ -11,14 +11,37 @@ RayTracer::RayTracer() {
 
 RayTracer::~RayTracer() { cleanup(); }
 
-int RayTracer::setupCL(int device_ordinal) {
+int RayTracer::setupCL(int device_ordinal, int n_gpus) {
     if (ctx_) return SDK_SUCCESS;
+    if (n_gpus > 1) {
+        if (rt_create_group(n_gpus, nullptr, &group_) != RT_OK) {
+            err_ = rt_group_last_error(nullptr);
+            group_ = nullptr;
+            return SDK_FAILURE;
+        }
+        ctx_ = rt_group_context(group_, 0);
+        n_gpus_ = n_gpus;
+        return SDK_SUCCESS;
+    }
     if (rt_create(device_ordinal, &ctx_) != RT_OK) {
         err_ = rt_last_error(nullptr);
         ctx_ = nullptr;
         return SDK_FAILURE;
     }
     return SDK_SUCCESS;
+}
+
+std::vector<double> RayTracer::last_rank_ms() const {
+    std::vector<double> ms;
+    double st[RT_GROUP_STATS];
+    if (group_ && rt_group_stats(group_, st) == RT_OK)
+        for (int r = 0; r < n_gpus_; r++) ms.push_back(st[RT_GROUP_STAT_RANK_KERNEL_MS + r]);
+    return ms;
+}
+
+double RayTracer::broadcast_ms() const {
+    double st[RT_GROUP_STATS];
+    return (group_ && rt_group_stats(group_, st) == RT_OK) ? st[RT_GROUP_STAT_BROADCAST_MS] : 0.0;
 }
 
 int RayTracer::initRayTrace(const char* collada_path) {
@@ -56,13 +79,20 @@ int RayTracer::upload() {
         err_ = "initRayTrace before setupCL";
         return SDK_FAILURE;
     }
-    const int rc = rt_upload_scene(ctx_, &mesh1.vertices[0].x, (int)mesh1.vertices.size(), mesh1.indices.data(), mesh1.getNumTriangles(),
+    const float* normals = mesh1.normals.empty() ? nullptr : &mesh1.normals[0].x;
+    int rc;
+    if (group_)
+        rc = rt_group_upload_scene(group_, &mesh1.vertices[0].x, (int)mesh1.vertices.size(), mesh1.indices.data(), mesh1.getNumTriangles(),
                                    bvh_cuda.bvh_nodes.data(), (int)bvh_cuda.bvh_nodes.size(), bvh_cuda.tri_indices.data(),
-                                   (int)bvh_cuda.tri_indices.size(), &mesh1.normals[0].x, (int)mesh1.normals.size(),
-                                   mesh1.normals_indices.data(), mesh1.materials.data(), (int)mesh1.materials.size(),
-                                   mesh1.triangle_index_to_material_index.data());
+                                   (int)bvh_cuda.tri_indices.size(), normals, (int)mesh1.normals.size(), mesh1.normals_indices.data(),
+                                   mesh1.materials.data(), (int)mesh1.materials.size(), mesh1.triangle_index_to_material_index.data());
+    else
+        rc = rt_upload_scene(ctx_, &mesh1.vertices[0].x, (int)mesh1.vertices.size(), mesh1.indices.data(), mesh1.getNumTriangles(),
+                             bvh_cuda.bvh_nodes.data(), (int)bvh_cuda.bvh_nodes.size(), bvh_cuda.tri_indices.data(),
+                             (int)bvh_cuda.tri_indices.size(), normals, (int)mesh1.normals.size(), mesh1.normals_indices.data(),
+                             mesh1.materials.data(), (int)mesh1.materials.size(), mesh1.triangle_index_to_material_index.data());
     if (rc != RT_OK) {
-        err_ = rt_last_error(ctx_);
+        err_ = group_ ? rt_group_last_error(group_) : rt_last_error(ctx_);
         return SDK_FAILURE;
     }
     return SDK_SUCCESS;
@@ -71,8 +101,8 @@ int RayTracer::upload() {
 int RayTracer::updateCamera() {
     cam.make_params(image_width, image_height, light_pos, light_color1, mesh1.scene_aabbox_min, mesh1.scene_aabbox_max, params);
     if (animate) cam.add_rotate(-0.25f * 1.5f * delta_t, 0.0f);  // the reference's orbit (RayTracer.cpp:657)
-    if (!ctx_ || rt_set_params(ctx_, params) != RT_OK) {
-        err_ = ctx_ ? rt_last_error(ctx_) : "updateCamera before setupCL";
+    if (!ctx_ || (group_ ? rt_group_set_params(group_, params) : rt_set_params(ctx_, params)) != RT_OK) {
+        err_ = !ctx_ ? "updateCamera before setupCL" : (group_ ? rt_group_last_error(group_) : rt_last_error(ctx_));
         return SDK_FAILURE;
     }
     return SDK_SUCCESS;
@@ -109,6 +139,13 @@ int RayTracer::raytrace_gpgpu() {
     while (inflight_ > 0)
         if (raytrace_gpgpu_end() != SDK_SUCCESS) return SDK_FAILURE;
     size_and_pin(out_data);
+    if (group_) {  // every GPU stores its row bands straight into out_data (page-locked, portable)
+        if (rt_render_frame_tiled(group_, image_width, image_height, out_data.data()) != RT_OK) {
+            err_ = rt_group_last_error(group_);
+            return SDK_FAILURE;
+        }
+        return SDK_SUCCESS;
+    }
     if (rt_render_frame(ctx_, image_width, image_height, out_data.data()) != RT_OK) {
         err_ = rt_last_error(ctx_);
         return SDK_FAILURE;
@@ -119,6 +156,10 @@ int RayTracer::raytrace_gpgpu() {
 int RayTracer::raytrace_gpgpu_begin() {
     if (!ctx_) {
         err_ = "raytrace_gpgpu_begin before setupCL";
+        return SDK_FAILURE;
+    }
+    if (group_) {
+        err_ = "raytrace_gpgpu_begin: frames in flight are a single-GPU feature; use raytrace_gpgpu() with a GPU group";
         return SDK_FAILURE;
     }
     if (inflight_ >= 2) {
@@ -156,9 +197,12 @@ int RayTracer::cleanup() {
         while (inflight_ > 0) raytrace_gpgpu_end();
         for (const auto& p : pinned_) rt_host_unregister(ctx_, p.first);
         pinned_.clear();
-        rt_destroy(ctx_);
+        if (group_) rt_destroy_group(group_);  // owns ctx_
+        else rt_destroy(ctx_);
     }
     ctx_ = nullptr;
+    group_ = nullptr;
+    n_gpus_ = 1;
     return SDK_SUCCESS;
 }
 

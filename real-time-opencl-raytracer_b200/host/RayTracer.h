@@ -2,11 +2,11 @@
 // gathered into the (there empty) `class RayTracer` (reference RayTracer.h:19-24).
 //
 //   reference (RayTracer.cpp)                              here
-//   setupCL()            :2370  context/queue/kernel        RayTracer::setupCL(device)     -> rt_create
+//   setupCL()            :2370  context/queue/kernel        RayTracer::setupCL(device, n)  -> rt_create / rt_create_group
 //   initRayTrace()       :858   load scene, build SBVH,     RayTracer::initRayTrace(...)   -> SplitBVHBuilder,
 //                                flatten, 11 clCreateBuffer                                    BVH_Cuda, rt_upload_scene
 //   updateCamera()       :609   Camera -> Params, write     RayTracer::updateCamera()      -> rt_set_params
-//   raytrace_gpgpu()     :330   NDRange + finish + readback RayTracer::raytrace_gpgpu()    -> rt_render_frame
+//   raytrace_gpgpu()     :330   NDRange + finish + readback RayTracer::raytrace_gpgpu()    -> rt_render_frame(_tiled)
 //   cleanup()            :1263                              RayTracer::cleanup()           -> rt_destroy
 //
 // Return convention as in the reference: SDK_SUCCESS (0) or SDK_FAILURE (1); the message is in last_error().
@@ -21,6 +21,7 @@
 #include "Mesh.h"
 
 struct rt_context;
+struct rt_group;
 
 #ifndef SDK_SUCCESS
 #define SDK_SUCCESS 0
@@ -47,7 +48,14 @@ public:
     RayTracer(const RayTracer&) = delete;
     RayTracer& operator=(const RayTracer&) = delete;
 
-    int setupCL(int device_ordinal = 0);
+    // n_gpus > 1: the frame is split in row bands over GPUs 0..n_gpus-1 of this box (rt_create_group: the scene is
+    // broadcast with NCCL over NVLink, every GPU stores its bands straight into out_data). The reference takes
+    // devices[0] only (RayTracer.cpp:2128-2131).
+    int setupCL(int device_ordinal = 0, int n_gpus = 1);
+    int gpus() const { return n_gpus_; }
+    // per-GPU device time of the last frame (ms) and the scene broadcast time, n_gpus > 1 only
+    std::vector<double> last_rank_ms() const;
+    double broadcast_ms() const;
     // scene from a COLLADA file (the reference loads data/collada/cubes2.DAE) ...
     int initRayTrace(const char* collada_path);
     // ... or from a Mesh the caller filled (synthetic scenes); `flat_bvh_cache` (optional) is read if present,
@@ -77,6 +85,8 @@ private:
     std::vector<unsigned int> ring_[2];
     int head_ = 0, inflight_ = 0;
     rt_context* ctx_ = nullptr;
+    rt_group* group_ = nullptr;   // n_gpus > 1; ctx_ is then GPU 0's context (borrowed from the group)
+    int n_gpus_ = 1;
     std::string err_;
     double build_seconds_ = 0.0;
 };

@@ -102,13 +102,21 @@ def close_shared_frame(dist, ctx, rank, ptr):
 
 
 class HostFrame:
-    """Framebuffer in POSIX shared memory that every rank page-locks and maps into its GPU: each rank's trace kernel
-    stores its bands straight into the consumer's HOST memory over its own PCIe link (rt_host_register). The frame is
-    complete on rank 0 -- without any device->host copy -- once every rank's kernel has finished."""
+    """Framebuffer(s) in POSIX shared memory that every rank page-locks and maps into its GPU: each rank's trace kernel
+    stores its bands straight into the consumer's HOST memory over its own PCIe link (rt_host_register). A frame is
+    complete on rank 0 -- without any device->host copy -- once every rank's kernel has finished; the ranks say so through
+    one sequence word each (rt_signal, stream-ordered behind the kernel) that rank 0 polls, instead of a barrier per
+    frame, and rank 0 publishes the last frame it has seen complete in an `ack` word so that nobody overwrites a frame
+    the consumer has not taken yet (`n_frames` buffers are cycled)."""
 
-    def __init__(self, dist, ctx, rank, h, w, dtype=np.int32):
-        self.dist, self.ctx, self.rank = dist, ctx, rank
-        nbytes = int(h) * int(w) * np.dtype(dtype).itemsize
+    CTRL_BYTES = 4096  # one 64-byte line per rank for its sequence word, the ack word in the last line
+
+    def __init__(self, dist, ctx, rank, h, w, dtype=np.int32, n_frames=1):
+        self.dist, self.ctx, self.rank, self.world = dist, ctx, rank, dist.get_world_size()
+        self.frame_bytes = int(h) * int(w) * np.dtype(dtype).itemsize
+        self.frame_stride = (self.frame_bytes + 4095) & ~4095
+        self.n_frames = n_frames
+        nbytes = self.frame_stride * n_frames + self.CTRL_BYTES
         box = [None]
         if rank == 0:
             try:
@@ -127,15 +135,52 @@ class HostFrame:
                 resource_tracker.unregister(self.shm._name, "shared_memory")
             except Exception:  # noqa: BLE001
                 pass
-        self.array = np.ndarray((h, w), dtype=dtype, buffer=self.shm.buf)
+        self.frames = [np.ndarray((h, w), dtype=dtype, buffer=self.shm.buf, offset=k * self.frame_stride) for k in range(n_frames)]
+        self.array = self.frames[0]
+        ctrl = self.frame_stride * n_frames
+        self.words = np.ndarray((self.CTRL_BYTES // 4,), dtype=np.uint32, buffer=self.shm.buf, offset=ctrl)
+        if rank == 0:
+            self.words[:] = 0
         self.host_ptr = ctypes.addressof(ctypes.c_char.from_buffer(self.shm.buf))
         self.nbytes = nbytes
         self.device_alias = ctx.host_register(self.host_ptr, nbytes)
+        self._ctrl_alias = self.device_alias + ctrl
+        dist.barrier()
+
+    def frame_alias(self, k):
+        return self.device_alias + (k % self.n_frames) * self.frame_stride
+
+    def signal(self, seq):
+        """enqueue on the context stream: this rank's sequence word <- seq once its part of the frame has landed"""
+        self.ctx.signal(self._ctrl_alias + 64 * self.rank, seq)
+
+    @staticmethod
+    def _spin(words, index, seq, what, timeout_s=60.0):
+        import time
+
+        spins, t0 = 0, None
+        while words[index] < seq:
+            spins += 1
+            if (spins & 0xFFFF) == 0:  # a dead peer must not hang the job
+                t0 = t0 or time.time()
+                if time.time() - t0 > timeout_s:
+                    raise TimeoutError(f"{what}: sequence word {index // 16} stayed at {int(words[index])}, waiting for {seq}")
+
+    def wait_frame(self, seq):
+        """rank 0: spin until every rank has signalled frame `seq`, then acknowledge it"""
+        for r in range(self.world):
+            self._spin(self.words, 16 * r, seq, "wait_frame")
+        self.words[16 * (self.CTRL_BYTES // 64 - 1)] = seq
+
+    def wait_ack(self, seq):
+        """any rank: spin until rank 0 has taken frame `seq`"""
+        self._spin(self.words, 16 * (self.CTRL_BYTES // 64 - 1), seq, "wait_ack")
 
     def close(self):
+        self.ctx.synchronize()
         self.ctx.host_unregister(self.host_ptr)
         self.dist.barrier()
-        self.array = None
+        self.array = self.frames = self.words = None
         try:
             self.shm.close()
         except BufferError:

@@ -177,35 +177,6 @@ def test_medium_scene_all_ray_classes_vs_oracle(ctx):
     assert d.max() <= 1 and (d.max(axis=-1) > 0).mean() < 0.02
 
 
-@pytest.mark.parametrize("name", ["mix", "terrain12", "ico2"])
-def test_wavefront_frame_equals_megakernel(ctx, name):
-    """rt_render_frame: the wavefront pipeline (default) and the one-thread-per-pixel megakernel give the same pixels, bit for
-    bit, with either scheduler for the bounce stages"""
-    import torch
-
-    g = load_scene(name)
-    _upload(ctx, g)
-    w, h = 160, 100
-    params, _ = rtb200.camera_params(w, h, g["aabb_min"], g["aabb_max"], light_pos=(-150.0, 25.0, 3.0))
-    ctx.set_params(params)
-    frames = []
-    try:
-        for mode, lanes in ((0, 0), (1, 0), (1, 1)):
-            ctx.set_option("frame_mode", mode)
-            ctx.set_option("wf_lanes", lanes)
-            img = torch.full((h, w), -1, dtype=torch.int32, device="cuda")
-            ctx.render_frame_device(w, h, img)
-            ctx.render_frame_device(w, h, img)  # a second frame re-uses the queues
-            ctx.synchronize()
-            frames.append(img.cpu())
-    finally:
-        ctx.set_option("frame_mode", 0)
-        ctx.set_option("wf_lanes", 1)
-    assert torch.equal(frames[0], frames[1]) and torch.equal(frames[0], frames[2])
-    ref_img, _ = O.OracleScene(mesh_dict(g), g["ref_nodes"], g["ref_tri_indices"]).render_frame(params, w, h)
-    assert channel_diff(frames[2].numpy().view(np.uint32), ref_img).max() <= 1
-
-
 def test_gate_pretest_never_drops_a_hit(ctx):
     """the conservative approximate scene-gate pre-test only skips pixels the exact gate rejects anyway: primary hits
     stay bit-identical to the oracle from far, near, inside-the-box, grazing and axis-parallel camera poses"""
@@ -597,16 +568,16 @@ def test_full_size_properties(ctx):
     assert np.all((h3["idx"] != hits["idx"][sel]) | (h3["t"] < hits["t"][sel]))
 
 
-@pytest.mark.parametrize("frame_mode", [0, 1])
+@pytest.mark.parametrize("overlap", [1, 0])
 @pytest.mark.parametrize("pinned", [True, False])
-def test_pipelined_frames_equal_frame_by_frame(ctx, pinned, frame_mode):
+def test_pipelined_frames_equal_frame_by_frame(ctx, pinned, overlap):
     """rt_render_frame_begin/_end with several frames in flight (each with its own Params block, set while earlier
     frames are still running) deliver exactly the frames rt_render_frame delivers one by one"""
     import torch
 
     g = load_scene("mix")
     _upload(ctx, g)
-    ctx.set_option("frame_mode", frame_mode)  # 0: one kernel per frame on per-slot streams; 1: wavefront pipeline on the context stream
+    ctx.set_option("overlap_frames", overlap)  # 1: every frame slot on its own stream (frames overlap on the GPU); 0: context stream
     w, h = (int(v) for v in g["wh"])
     frames = []
     for k in range(6):  # orbit: rotate a, b, c, campos about the y axis
@@ -636,7 +607,7 @@ def test_pipelined_frames_equal_frame_by_frame(ctx, pinned, frame_mode):
         ctx.render_frame_end(k % slots)
         b = bufs[k % slots]
         got[k] = (b.numpy().view(np.uint32) if pinned else b).copy()
-    ctx.set_option("frame_mode", 0)
+    ctx.set_option("overlap_frames", 1)
     for k in range(len(frames)):
         assert np.array_equal(got[k], want[k]), f"frame {k}"
     ctx.set_params(g["params"])

@@ -69,14 +69,14 @@ for seed in range(100, 100 + nseeds):
     params, _ = rtb200.camera_params(w, h, A["aabb_min"], A["aabb_max"], d_radius=float(np.linalg.norm(A["aabb_max"] - A["aabb_min"])) - 200.0)
     ctx.set_params(params)
     ref, _ = sc.render_frame(params, w, h)
-    for fm in (0, 1):
-        ctx.set_option("frame_mode", fm)
+    for fm in (0, 4):  # directly stored and row-assembled frames
+        ctx.set_option("store_group", fm)
         img = ctx.render_frame(w, h)
         df = np.abs(img.view(np.uint8).astype(int) - ref.view(np.uint8).astype(int)).max()
         if df > 1:
             bad += 1
             print(f"FRAME seed {seed} scale {scale} mode {fm}: max diff {df}")
-    ctx.set_option("frame_mode", 0)
+    ctx.set_option("store_group", -1)
     print(f"seed {seed} scale {scale:g} tris {nt} hoisted={info['hoisted_division']} hit {float((want['idx'] >= 0).mean()):.3f} ok", flush=True)
 print(f"fuzz done: {total} ray comparisons, {bad} mismatches")
 sys.exit(1 if bad else 0)
