@@ -63,9 +63,15 @@ bool ColladaLoader::load(const char* filename) {
         return false;
     }
     load_effects(child(collada, "library_effects"));
-    load_geometries(collada);
+    if (!load_geometries(collada) && !error_.empty()) return false;
     load_visual_scenes(collada);
     compute_geometry_to_scene_index();
+    for (const Geometry& g : library_geometries)
+        for (const PolygonTriangle& t : g.polygons)
+            if (t.effect_index < 0 || (size_t)t.effect_index >= library_effects.size()) {
+                error_ = "a <polygons> element names a material that no <effect> defines";
+                return false;
+            }
     return true;
 }
 
@@ -102,7 +108,8 @@ bool ColladaLoader::load_geometries(const Node* collada) {
     const Node* lib = child(collada, "library_geometries");
     if (!lib) return false;
     int count = 0;
-    for (const Node* g = lib->child("geometry"); g; g = g->next_sibling("geometry"), ++count) load_geometry(g, count);
+    for (const Node* g = lib->child("geometry"); g; g = g->next_sibling("geometry"), ++count)
+        if (!load_geometry(g, count)) return false;
     return true;
 }
 
@@ -119,10 +126,22 @@ const Node* float_array_of(const Node* mesh, const std::string& source_id) {
         if (source_id == attr(s, "id")) return s->child("float_array");
     return nullptr;
 }
-template <class V> void read_array(const Node* float_array, int comps, std::vector<V>& out) {
-    const int num_floats = atoi(attr(float_array, "count"));
-    out.resize(num_floats / comps);
-    if (!out.empty()) stof_array(text(float_array), num_floats, out[0].m);
+// `count` comes from the file: it is trusted only as far as the text can back it (a float needs at least two
+// characters, digit + separator) and only whole elements are parsed, so a count that is negative, absurd or not a
+// multiple of `comps` can neither throw out of resize() nor write past the vector.
+template <class V> bool read_array(const Node* float_array, int comps, std::vector<V>& out) {
+    out.clear();
+    if (!float_array) return true;  // a missing optional source (e.g. no TEXCOORD) is not an error
+    const long long num_floats = atoll(attr(float_array, "count"));
+    const std::string& txt = text(float_array);
+    if (num_floats < 0 || num_floats > (long long)(txt.size() + 1) / 2 + 1) return false;
+    const size_t elems = (size_t)(num_floats / comps);
+    out.resize(elems);
+    if (elems == 0) return true;
+    static_assert(sizeof(V) % sizeof(float) == 0, "V is a plain float vector");
+    if (sizeof(V) != sizeof(float) * (size_t)comps) return false;
+    stof_array(txt, (int)(elems * comps), out[0].m);  // a short text leaves zeros, as resize() made them
+    return true;
 }
 }  // namespace
 
@@ -142,21 +161,39 @@ bool ColladaLoader::load_geometry(const Node* geo, int count) {
             pos_id = strip_hash(attr(v->child("input"), "source"));
             break;
         }
-    read_array(float_array_of(mesh, pos_id), 3, g.float_array_positions);
-    read_array(float_array_of(mesh, input_source(polys, "NORMAL")), 3, g.float_array_normals);
-    read_array(float_array_of(mesh, input_source(polys, "TEXCOORD")), 2, g.float_array_uv0);
-
+    const bool arrays_ok = read_array(float_array_of(mesh, pos_id), 3, g.float_array_positions) &&
+                           read_array(float_array_of(mesh, input_source(polys, "NORMAL")), 3, g.float_array_normals) &&
+                           read_array(float_array_of(mesh, input_source(polys, "TEXCOORD")), 2, g.float_array_uv0);
+    if (!arrays_ok) {
+        error_ = std::string("geometry '") + attr(geo, "id") + "': float_array count does not match its text";
+        return false;
+    }
+    // Index ranges are checked here, before anything (Mesh::init, the SBVH builder) dereferences them.
+    for (const PolygonTriangle& t : g.polygons)
+        for (int k = 0; k < 3; ++k) {
+            const int vi = t.vertex_indices.m[k], ni = t.normal_indices.m[k];
+            if (vi < 0 || (size_t)vi >= g.float_array_positions.size() || ni < 0 ||
+                (!g.float_array_normals.empty() && (size_t)ni >= g.float_array_normals.size()) ||
+                (g.float_array_normals.empty() && ni != 0)) {
+                error_ = std::string("geometry '") + attr(geo, "id") + "': <p> index out of range";
+                return false;
+            }
+        }
     library_geometries.push_back(std::move(g));
     return true;
 }
 
 // every <p> holds one triangle as "v n t v n t v n t"
 bool ColladaLoader::load_polygons(const Node* polys, Geometry& g) {
-    const int num = atoi(attr(polys, "count"));
+    long long num = atoll(attr(polys, "count"));
+    long long have = 0;  // a count larger than the <p> elements present is clamped: nothing to read there
+    for (const Node* q = child(polys, "p"); q; q = q->next_sibling("p")) ++have;
+    if (num < 0) num = 0;
+    if (num > have) num = have;
     const int effect_index = effect_name_to_index_[attr(polys, "material")];
-    g.polygons.resize(num > 0 ? num : 0);
+    g.polygons.resize((size_t)num);
     const Node* p = child(polys, "p");
-    for (int i = 0; i < num; ++i) {
+    for (long long i = 0; i < num; ++i) {
         PolygonTriangle& t = g.polygons[i];
         t.effect_index = effect_index;
         if (p) {

@@ -52,3 +52,17 @@ def assert_hits_identical(got, want, what=""):
 def channel_diff(img_a, img_b):
     sh = np.array([0, 8, 16])
     return np.abs(((img_a[..., None] >> sh) & 255).astype(np.int32) - ((img_b[..., None] >> sh) & 255).astype(np.int32))
+
+
+def gpu_context(device=0):
+    """A context whose kernels run on torch's current stream. The tests hand torch tensors to the device entry points; a
+    context on its own (non-blocking) stream would race torch's asynchronous fills of those tensors (torch.zeros is a
+    kernel on torch's stream): a 66 MB zero-fill once landed AFTER the primary pass had written the rays. A caller that
+    mixes frameworks orders the streams itself -- that is what rt_set_stream is for (include/rtb200.h)."""
+    import torch
+
+    import rtb200
+
+    c = rtb200.Context(device)
+    c.set_stream(torch.cuda.current_stream(device).cuda_stream)
+    return c

@@ -3,7 +3,7 @@
 multi-GPU group. Bar as everywhere: bit-identical to the two-pass path, to the golden fixtures and to the live oracle."""
 import numpy as np
 import pytest
-from conftest import SCENES, assert_hits_identical, load_scene, mesh_dict
+from conftest import SCENES, assert_hits_identical, load_scene, mesh_dict, gpu_context
 
 import rtb200
 from oracle import oracle_py as O
@@ -14,7 +14,7 @@ HIT = rtb200.HIT_DTYPE
 
 @pytest.fixture(scope="module")
 def ctx():
-    c = rtb200.Context(0)
+    c = gpu_context()
     yield c
     c.close()
 

@@ -3,7 +3,7 @@ golden fixtures. Bar: bit-exact hit index, t, u, v (integer/index work AND the f
 kernels keep the reference's operation order with FMA contraction off); frames within +-1 LSB (powf)."""
 import numpy as np
 import pytest
-from conftest import SCENES, assert_hits_identical, channel_diff, load_scene, mesh_dict, same_bits
+from conftest import SCENES, assert_hits_identical, channel_diff, load_scene, mesh_dict, same_bits, gpu_context
 
 import rtb200
 from oracle import oracle_py as O
@@ -14,7 +14,7 @@ HIT = rtb200.HIT_DTYPE
 
 @pytest.fixture(scope="module")
 def ctx():
-    c = rtb200.Context(0)
+    c = gpu_context()
     yield c
     c.close()
 

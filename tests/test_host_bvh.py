@@ -112,6 +112,49 @@ def test_collada_roundtrip(tmp_path):
     assert same_bits(A["aabb_min"], B["aabb_min"]) and same_bits(A["aabb_max"], B["aabb_max"])
 
 
+@pytest.mark.parametrize("damage", ["count_not_multiple", "count_huge", "count_negative", "vertex_index", "normal_index",
+                                    "material_name", "p_count_huge"])
+def test_collada_malformed_files_fail_cleanly(tmp_path, damage):
+    """a float_array count that the text cannot back, or <p> indices / material names that point nowhere,
+    must fail the load (IOError through rth_mesh_load_dae) -- no heap overflow, no exception through extern "C", no
+    out-of-range index handed to the SBVH builder."""
+    import re
+    m = rtb200.Mesh().icosphere(1, 10.0).finish(diffuse=(0.25, 0.5, 0.75))
+    p = str(tmp_path / "ok.dae")
+    m.write_dae(p)
+    txt = open(p).read()
+    counts = re.findall(r'<float_array[^>]*count="(\d+)"', txt)
+    assert counts, "generated file has float arrays"
+    first = f'count="{counts[0]}"'
+    if damage == "count_not_multiple":   # was: 1-2 floats written past the allocation; now the tail is ignored
+        bad = txt.replace(first, f'count="{int(counts[0]) - 1}"', 1)
+    elif damage == "count_huge":
+        bad = txt.replace(first, 'count="2000000000"', 1)
+    elif damage == "count_negative":
+        bad = txt.replace(first, 'count="-5"', 1)
+    elif damage == "vertex_index":
+        bad = re.sub(r"<p>\s*(\d+) ", "<p>999999 ", txt, count=1)
+    elif damage == "normal_index":
+        bad = re.sub(r"<p>\s*(\d+) (\d+) ", r"<p>\1 -7 ", txt, count=1)
+    elif damage == "material_name":
+        bad = re.sub(r'(<polygons[^>]*material=")[^"]*"', r'\1no_such_effect"', txt, count=1)
+        bad = re.sub(r"<library_effects>.*</library_effects>", "<library_effects></library_effects>", bad, flags=re.S)
+    else:
+        bad = re.sub(r'(<polygons[^>]*count=")\d+"', r'\g<1>2000000000"', txt, count=1)
+    assert bad != txt
+    q = str(tmp_path / "bad.dae")
+    open(q, "w").write(bad)
+    if damage in ("count_not_multiple", "p_count_huge"):
+        try:   # either the load fails, or what it delivers is in range
+            B = rtb200.Mesh().load_dae(q).arrays()
+        except IOError:
+            return
+        assert B["indices"].size == 0 or B["indices"].max() < B["verts"].shape[0]
+    else:
+        with pytest.raises(IOError):
+            rtb200.Mesh().load_dae(q)
+
+
 REF_CUBES2 = "/root/reference/x64/Release/data/collada/cubes2.DAE"
 
 
