@@ -255,6 +255,11 @@ int rt_set_option(rt_context* ctx, const char* name, int value);
 int rt_selftest(rt_context* ctx, int64_t samples, uint32_t seed, uint64_t* out_mismatches);
 /* Same comparison with the numerator's binary exponent fixed (probe of the admitted operand window). */
 int rt_selftest_range(rt_context* ctx, int64_t samples, uint32_t seed, int x_exponent, uint64_t* out_mismatches);
+/* Exhaustive form: ALL 2^23 numerator mantissas x md_count divisor mantissas from md_begin (chunks of <= 65535; the full
+ * square is 2^46 quotients, about a GPU-minute) at binary exponents ex_x / ex_d and signs (bit 0: divisor < 0, bit 1:
+ * numerator < 0). Power-of-two scaling is exact inside the window, so one exponent pair stands for all. */
+int rt_selftest_exhaustive(rt_context* ctx, uint32_t md_begin, uint32_t md_count, int ex_x, int ex_d, uint32_t signs,
+                           uint64_t* out_mismatches);
 /* Scene statistics: [0] node pairs, [1] packed triangles, [2] blob bytes, [3] max tree depth,
  * [4] 1 if every box coordinate admits the hoisted exact division (else the full division is used), [5] BFS-ordered pairs */
 int rt_scene_info(rt_context* ctx, int64_t out[6]);

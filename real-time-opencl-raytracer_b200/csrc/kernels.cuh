@@ -50,7 +50,35 @@ struct TraceArgs {
     unsigned int* group_count;  // one arrival counter per (tile row of this rank, group), zeroed before launch
     int group_log2;             // 0 = off, 2 = 4 tiles (32 px), 4 = 16 tiles (128 px)
     int groups_x;
+#ifdef RTB_TIMELINE
+    unsigned long long* timeline;  // tools build only: {start ns, end ns | smid << 56} per batch (tools/timeline_probe.py)
+#endif
 };
+
+#ifdef RTB_TIMELINE
+__device__ __forceinline__ unsigned long long tl_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned int tl_smid() {
+    unsigned int s;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+    return s;
+}
+#define RTB_TL_BEGIN(a) const unsigned long long tl_t0__ = (a).timeline ? tl_now() : 0ull
+#define RTB_TL_END(a, batch, lane)                                                              \
+    do {                                                                                        \
+        __syncwarp();                                                                           \
+        if ((a).timeline && (lane) == 0) {                                                      \
+            (a).timeline[2 * (batch)] = tl_t0__;                                                \
+            (a).timeline[2 * (batch) + 1] = (tl_now() & 0x00ffffffffffffffull) | ((unsigned long long)tl_smid() << 56); \
+        }                                                                                       \
+    } while (0)
+#else
+#define RTB_TL_BEGIN(a)
+#define RTB_TL_END(a, batch, lane)
+#endif
 
 #ifndef RTB_MINB_BATCH
 #define RTB_MINB_BATCH 1
@@ -195,6 +223,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
         if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
         batch = __shfl_sync(0xffffffffu, batch, 0);
         if (batch >= (unsigned long long)a.num_batches) break;
+        RTB_TL_BEGIN(a);
 
         Ray ray;
         float tmax = RTB_T_INIT;
@@ -256,6 +285,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
             if (SRC == SRC_PRIMARY && a.frame_out) pixel_sink(a)[out_index] = (unsigned int)r.idx;
         }
         if (SRC == SRC_PRIMARY && a.frame_out) finish_tile(a, tile_x, tile_k, tile_y0, lane);
+        RTB_TL_END(a, batch, lane);
     }
     retire_ray_count(a, traced, lane);
 }
@@ -276,6 +306,7 @@ __global__ void __launch_bounds__(kBlockThreads) primary_shadow_kernel(const Tra
         if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
         batch = __shfl_sync(0xffffffffu, batch, 0);
         if (batch >= (unsigned long long)a.num_batches) break;
+        RTB_TL_BEGIN(a);
         int x, y, tx;
         long long k;
         tile_pixel(a, (long long)batch, lane, x, y, tx, k);
@@ -301,6 +332,7 @@ __global__ void __launch_bounds__(kBlockThreads) primary_shadow_kernel(const Tra
             if (a.frame_out) pixel_sink(a)[px] = hit.idx < 0 ? 0xffffffffu : (unsigned int)(hit.idx + ((sh.idx >= 0 && sh.t > 0.025f) ? 1 : 0));
         }
         if (a.frame_out) finish_tile(a, tx, k, y - (lane >> 3), lane);
+        RTB_TL_END(a, batch, lane);
     }
     retire_ray_count(a, traced, lane);
 }
@@ -623,5 +655,47 @@ __global__ void selftest_division_kernel(unsigned int seed, int iters, unsigned 
     }
     if (bad) atomicAdd(mismatches, bad);
 }
+
+
+// Exhaustive form of the self test: EVERY mantissa pair (2^23 x 2^23 = 2^46 quotients) at one exponent / sign pair.
+// Scaling either operand by a power of two scales the quotient, every intermediate of the hoisted sequence and every
+// rounding boundary by the same power of two (no overflow / underflow inside the admitted window, which the range
+// probe establishes), so one exponent pair stands for all of them. blockIdx.y selects the divisor mantissa md0 + y,
+// the x dimension strides over all 2^23 numerator mantissas.
+__global__ void selftest_division_exhaustive_kernel(unsigned int md0, int ex_x, int ex_d, unsigned int signs,
+                                                    unsigned long long* mismatches) {
+    const unsigned int md = md0 + blockIdx.y;
+    const float d = __uint_as_float(((signs & 1u) << 31) | ((unsigned int)(ex_d + 127) << 23) | (md & 0x7FFFFFu));
+    const float r1 = div_prepare(d);
+    const f32x2 nd2 = pack2(-d, -d), r2 = pack2(r1, r1);
+    const unsigned int xs = ((signs >> 1) & 1u) << 31 | ((unsigned int)(ex_x + 127) << 23);
+    unsigned int bad = 0;
+    for (unsigned int mx = blockIdx.x * blockDim.x + threadIdx.x; mx < (1u << 23); mx += gridDim.x * blockDim.x) {
+        const float x = __uint_as_float(xs | mx);
+        const float want = x / d;
+        const float got = div_hoisted(x, d, r1);
+        float g0, g1;
+        unpack2(div_hoisted2_core(pack2(x, -x), nd2, r2), g0, g1);
+        bad += (__float_as_uint(want) != __float_as_uint(got)) + (__float_as_uint(want) != __float_as_uint(g0)) +
+               (__float_as_uint(-want) != __float_as_uint(g1));
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+// ---- SASS probes (tests/test_sass.py reads them with cuobjdump; they are never launched) ---------------------------
+// probe_ray_triangle_kernel holds exactly one inlined ray_triangle(); probe_reciprocal_kernel exactly one IEEE 1.0f / x.
+// If ptxas contracted any product-sum of Moller-Trumbore into an FFMA, the first kernel would show more FFMAs than the
+// division's own fixed-up reciprocal sequence, and fewer than 27 FMUL / 18 FADD.
+__global__ void probe_ray_triangle_kernel(const float4* __restrict__ in, float4* __restrict__ out) {
+    const float4 o = in[0], d = in[1], a = in[2], b = in[3], c = in[4];
+    Ray r;
+    r.ori = ld3(o);
+    r.dir = ld3(d);
+    float u = 0.0f, v = 0.0f;
+    const float t = ray_triangle(r, ld3(a), ld3(b), ld3(c), u, v);
+    out[0] = make_float4(t, u, v, 0.0f);
+}
+__global__ void probe_reciprocal_kernel(const float* __restrict__ in, float* __restrict__ out) { out[0] = 1.0f / in[0]; }
 
 }  // namespace rtb

@@ -79,6 +79,9 @@ struct rt_context {
     int opt_store_group = -1;   // row assembly of 4-byte/pixel frames: -1 = auto (on when the frame is host or peer memory),
                                 // 0 = off, 2 = groups of 4 tiles (128-byte rows), 4 = groups of 16 tiles (512-byte rows)
     uint64_t counters[RT_CNT_COUNT] = {0};
+#ifdef RTB_TIMELINE
+    unsigned long long* d_timeline = nullptr;  // tools build only (see kernels.cuh)
+#endif
     // resident blocks per SM of each kernel (occupancy query is a slow host call: done once per kernel and smem size)
     struct OccEntry { const void* fn; size_t smem; int per_sm; } occ_cache[32];
     int occ_count = 0;
@@ -433,6 +436,9 @@ static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, size_t sme
     if (blocks < 1) return RT_OK;  // nothing to do
     a.work_counter = counter;
     a.ray_counter = ctx->d_counter + kRayCounterSlot;
+#ifdef RTB_TIMELINE
+    a.timeline = ctx->d_timeline;
+#endif
     CK(ctx, cudaMemsetAsync(counter, 0, zero_bytes, stream));  // queue head (+ the row-assembly arrival counters behind it)
     kernel<<<(unsigned)blocks, kBlockThreads, smem, stream>>>(a, extra...);
     CK(ctx, cudaGetLastError());
@@ -1072,6 +1078,35 @@ extern "C" int rt_selftest_range(rt_context* ctx, int64_t samples, uint32_t seed
     *out_mismatches = bad;
     return RT_OK;
 }
+
+// Exhaustive self test: all 2^23 numerator mantissas against `md_count` divisor mantissas starting at md_begin, at the
+// exponents (ex_x, ex_d) and signs (bit 0: divisor negative, bit 1: numerator negative). The full square is 2^23
+// divisor mantissas; callers split it into chunks (tools/div_exhaustive.py) so that a launch stays short.
+extern "C" int rt_selftest_exhaustive(rt_context* ctx, uint32_t md_begin, uint32_t md_count, int ex_x, int ex_d, uint32_t signs,
+                                      uint64_t* out_mismatches) {
+    if (!ctx || !out_mismatches) return RT_E_INVALID;
+    if (md_count < 1 || md_count > 65535u || md_begin > (1u << 23) - md_count || ex_x < -100 || ex_x > 60 || ex_d < -20 || ex_d > 19)
+        return set_err(ctx, RT_E_INVALID, "rt_selftest_exhaustive: chunk of 1..65535 divisor mantissas inside [0, 2^23); exponents inside the window");
+    ON_DEVICE(ctx);
+    CK(ctx, cudaMemsetAsync(ctx->d_counter + 8, 0, sizeof(unsigned long long), ctx->stream));
+    selftest_division_exhaustive_kernel<<<dim3(16, md_count), 256, 0, ctx->stream>>>(md_begin, ex_x, ex_d, signs, ctx->d_counter + 8);
+    CK(ctx, cudaGetLastError());
+    unsigned long long bad = 0;
+    CK(ctx, cudaMemcpyAsync(&bad, ctx->d_counter + 8, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_mismatches = bad;
+    return RT_OK;
+}
+
+#ifdef RTB_TIMELINE
+// tools build only (make timeline): per-batch start/end timestamps of the persistent-warp kernels go to d_buf
+// (2 x uint64 per batch of the next launches; NULL = off)
+extern "C" int rt_debug_timeline(rt_context* ctx, void* d_buf) {
+    if (!ctx) return RT_E_INVALID;
+    ctx->d_timeline = (unsigned long long*)d_buf;
+    return RT_OK;
+}
+#endif
 
 // Host-only: validate + pack the reference arrays into the blob layout WITHOUT touching a device (the packing is
 // what rt_upload_scene uploads). For tools and the CPU tests of the layout; free the result with rt_free_host.

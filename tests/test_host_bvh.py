@@ -99,6 +99,97 @@ def test_camera_default_pose_and_params():
     assert np.allclose(p[4, :3], [-23, 200, 3]) and np.allclose(p[6, :3], [-1, -2, -3]) and np.allclose(p[7, :3], [4, 5, 6])
 
 
+# ---- bit-level pin of Camera + make_params (task 5e / weak 9) -------------------------------------------
+# A numpy restatement in explicit fp32 of reference Camera.cpp:6-68 and RayTracer.cpp:634-671 (updateCamera), operation
+# for operation. Double sub-expressions of the source (M_PI, the 3.1415 literal) are evaluated in double and rounded where
+# the source assigns them to a float. cos / sin / tan of a float are taken as the correctly rounded fp32 value (computed
+# in double, rounded once) -- the reference calls its C library's float overloads, whose last bit is not specified; glibc's
+# cosf / sinf / tanf agree with the correctly rounded value on every pose below.
+F = np.float32
+
+
+def _f3(x, y, z):
+    return np.array([x, y, z], dtype=np.float32)
+
+
+def _dot(a, b):
+    return F(F(F(a[0] * b[0]) + F(a[1] * b[1])) + F(a[2] * b[2]))             # vectors_math.cpp:73-75
+
+
+def _cross(a, b):
+    return _f3(F(F(a[1] * b[2]) - F(a[2] * b[1])), F(F(a[2] * b[0]) - F(a[0] * b[2])), F(F(a[0] * b[1]) - F(a[1] * b[0])))  # :77-79
+
+
+def _normalize(v):
+    inv = F(F(1.0) / np.sqrt(_dot(v, v), dtype=np.float32))                    # rsqrtf = 1.0f / sqrtf, :18-20, 81-84
+    return _f3(F(inv * v[0]), F(inv * v[1]), F(inv * v[2]))
+
+
+def _trig(fn, x):
+    import math
+    return F(fn(float(x)))
+
+
+def params_restated(w, h, light_pos, light_color, aabb_min, aabb_max, d_radius=0.0, rotations=()):
+    import math
+    PI = math.pi
+    radius, alpha, beta = F(200.0), F(0.0), F(0.0)
+    up = _f3(0, 1, 0)
+    center = _f3(0, 0, 0)
+
+    def add_rotate(da, db):                                                     # Camera.cpp:26-48
+        nonlocal alpha, beta, up
+        alpha = F(alpha + F(da))
+        beta = F(beta + F(db))
+        if beta < F(0.0):
+            beta = F(float(beta) + 2.0 * PI)                                    # float += double
+        elif float(beta) > 2.0 * PI:
+            beta = F(float(beta) - 2.0 * PI)
+        flipped = (float(beta) > PI / 2.0) and (float(beta) < 3.0 * PI / 2.0)
+        up = _f3(0, -1 if flipped else 1, 0)
+
+    add_rotate(F(45 * (3 + 2) * PI / 180.0), F(45 * PI / 180.0))                # Camera.cpp:18
+    if d_radius:
+        radius = F(radius + F(d_radius))                                        # add_radius, :21-24
+    for da, db in rotations:
+        add_rotate(F(da), F(db))
+    cb, sb = _trig(math.cos, beta), _trig(math.sin, beta)                       # update_eye, :50-59
+    eye = _f3(F(center[0] + F(F(radius * cb) * _trig(math.cos, alpha))),
+              F(center[1] + F(radius * sb)),
+              F(center[2] + F(F(radius * cb) * _trig(math.sin, alpha))))
+    direction = _normalize(_f3(*(F(center[i] - eye[i]) for i in range(3))))     # update_full, :61-68
+    right = _normalize(_cross(direction, up))
+    cr = _cross(direction, right)
+    cam_up = _normalize(_f3(-cr[0], -cr[1], -cr[2]))
+    theta = F((60.0 * 3.1415 * 0.5) / 180.0)                                    # RayTracer.cpp:639-640
+    half = _trig(math.tan, theta)
+    aspect = F(F(w) / F(h))
+    u0, v0 = F(F(-half) * aspect), F(-half)
+    u1, v1 = F(half * aspect), half
+    du, dv = F(u1 - u0), F(v1 - v0)
+    a = _f3(*(F(du * right[i]) for i in range(3)))                              # :650-652
+    b = _f3(*(F(dv * cam_up[i]) for i in range(3)))
+    c = _f3(*(F(F(F(eye[i] + F(u0 * right[i])) + F(v0 * cam_up[i])) + F(F(1.0) * direction[i])) for i in range(3)))
+    out = np.ones((8, 4), dtype=np.float32)
+    for i, row in enumerate((a, b, c, eye, light_pos, light_color, aabb_min, aabb_max)):
+        out[i, :3] = np.asarray(row, dtype=np.float32)
+    return out.reshape(-1), eye
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (1920, 1080), (3840, 2160), (1024, 768), (328, 204)])
+@pytest.mark.parametrize("pose", [dict(), dict(d_radius=1320.0), dict(d_alpha=0.3, d_beta=-0.2), dict(d_alpha=-2.5, d_beta=0.61),
+                                  dict(d_radius=-50.0, d_alpha=1.0, d_beta=0.5), dict(d_alpha=0.0, d_beta=1.0)])
+def test_camera_params_bit_identical_to_the_restated_reference(w, h, pose):
+    """Camera::Camera / add_radius / add_rotate / make_params == reference Camera.cpp + updateCamera in fp32, bit for bit
+    (the golden frames and every parity test inherit these 128 bytes)"""
+    light, colour, lo, hi = (-23.0, 200.0, 3.0), (1.0, 1.0, 1.0), (-100.0, -7.4, -100.0), (100.0, 7.4, 100.0)
+    got, eye = rtb200.camera_params(w, h, lo, hi, light_pos=light, light_color=colour, **pose)
+    rot = [(pose.get("d_alpha", 0.0), pose.get("d_beta", 0.0))] if ("d_alpha" in pose or "d_beta" in pose) else []
+    want, weye = params_restated(w, h, light, colour, lo, hi, d_radius=pose.get("d_radius", 0.0), rotations=rot)
+    assert same_bits(eye, weye), (eye, weye)
+    assert same_bits(got, want), np.flatnonzero(got.view(np.uint32) != want.view(np.uint32))
+
+
 def test_collada_roundtrip(tmp_path):
     """generated .dae -> ColladaLoader -> Mesh::init reproduces the mesh exactly (BASELINE config 1 path)"""
     m = rtb200.Mesh().icosphere(2, 50.0).finish(diffuse=(0.25, 0.5, 0.75))
