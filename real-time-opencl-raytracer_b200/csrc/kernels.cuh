@@ -50,6 +50,12 @@ struct TraceArgs {
     unsigned int* group_count;  // one arrival counter per (tile row of this rank, group), zeroed before launch
     int group_log2;             // 0 = off, 2 = 4 tiles (32 px), 4 = 16 tiles (128 px)
     int groups_x;
+    // Temporal tile scheduling (camera-ray kernels; see "tile scheduler" below): what the previous launch of this frame
+    // geometry learnt about its tiles, and where this launch records the same for the next one. Either may be NULL.
+    const unsigned int* hint_in;
+    unsigned int* hint_out;
+    int hint_heavy_pct, hint_light_pct;   // the slowest / quickest N percent of the tiles that traced
+    int hint_split_pct, hint_keep_pct;    // percent of the previous launch's span
 #ifdef RTB_TIMELINE
     unsigned long long* timeline;  // tools build only: {start ns, end ns | smid << 56} per batch (tools/timeline_probe.py)
 #endif
@@ -170,7 +176,7 @@ __device__ __forceinline__ unsigned int* pixel_sink(const TraceArgs& a) { return
 // Row assembly (see TraceArgs::stage). Called by ALL lanes of a warp after they stored their tile's pixels to the stage.
 // Last-arriver pattern: fence, count the tile in, and the warp that completes the group copies it out. The stage was
 // written by other SMs, so it is read around L1 (ld.global.cg).
-__device__ __forceinline__ void finish_tile(const TraceArgs& a, int tx, long long k, int y0, int lane) {
+__device__ __forceinline__ void finish_tile(const TraceArgs& a, int tx, long long k, int y0, int lane, unsigned int rows_done = 4u) {
     if (!a.group_log2) return;
     __threadfence();
     __syncwarp();
@@ -178,9 +184,10 @@ __device__ __forceinline__ void finish_tile(const TraceArgs& a, int tx, long lon
     const int first_tile = gx << a.group_log2;
     const int tiles_in_group = min(1 << a.group_log2, a.tiles_x - first_tile);
     unsigned int arrived = 0;
-    if (lane == 0) arrived = atomicAdd(a.group_count + k * a.groups_x + gx, 1u);
+    // arrivals are counted in pixel rows (4 per tile): a tile may arrive in pieces (tile scheduler: quarter / partial tiles)
+    if (lane == 0) arrived = atomicAdd(a.group_count + k * a.groups_x + gx, rows_done);
     arrived = __shfl_sync(0xffffffffu, arrived, 0);
-    if ((int)arrived + 1 != tiles_in_group) return;
+    if ((int)(arrived + rows_done) != 4 * tiles_in_group) return;
     __threadfence();
     const int x0 = first_tile * 8;
     const int span = tiles_in_group * 8;  // pixels per row of this group
@@ -201,6 +208,164 @@ __device__ __forceinline__ void finish_tile(const TraceArgs& a, int tx, long lon
     }
 }
 
+
+// ---- tile scheduler: persistent warps + temporal hints ------------------------------------------------------------------
+// A camera-ray launch is a queue of 8x4-pixel tiles drained by persistent warps. Measured on the bench frame (per-tile
+// timestamps, tools/timeline_probe.py): the median tile takes ~18 us but tiles whose rays skim a terrain ridge take 8x
+// that (every lane ~100 node visits + ~50 triangle tests, and the lanes drift apart); wherever they sit in the queue they
+// finish last, and a launch ends with 30-50 % of its duration spent at a few percent occupancy -- the tail that limits a
+// frame split over 8 GPUs. A real-time renderer draws almost the same frame again, so every launch RECORDS what it
+// learnt for the next launch of the same frame geometry (host side: rtb200.cu, hint slots):
+//   * the launch's span (longest life of a persistent warp), per tile the time it took (SM clock) and a histogram of those
+//     times. The slowest `heavy_pct` percent of the tiles go on the HEAVY list; a tile that took more than `split_pct`
+//     percent of the previous launch's span -- one that by itself decides when the launch ends -- goes on the SPLIT list
+//     as four one-row (8x1 pixel) items
+//     as four one-row (8x1 pixel) items; the quickest `light_pct` percent (of the tiles that traced at all) go on the
+//     LIGHT list
+//   * the next launch's queue is [split rows][heavy tiles][all tiles in row-major order, minus what the lists cover]
+//     [light tiles], the lists walked longest-first: the long tiles start first, the longest run as four warps with 8
+//     coherent lanes each instead of one warp whose 32 lanes serialise each other, and the launch ends on its shortest
+//     tiles, so the idle time at the end is a short tile's duration instead of a long one's
+// Hints only change WHO traces a pixel and WHEN; every pixel is still traced exactly once with the same arithmetic, so
+// results do not depend on them (tests/test_gpu_sched.py). A stale hint (the camera moved) costs time, never correctness.
+//
+// Hint buffer (32-bit words): [0] split entries [1] heavy entries [2] tiles timed [3] launch span (cycles) [4] light
+// entries; [16, 16 + 128) histogram of tile times in bins of 4096 cycles;  [H ..) split list: (batch << 2) | row;
+// [H + 4B ..) heavy list: batch;  [H + 5B ..) light list: batch;  [H + 6B ..) one byte per (batch, row): non-zero = that
+// row is covered by a list entry (H = kHintHeader, B = num_batches; the lists can hold every row / tile: no overflow).
+enum { kHintHist = 16, kHintBins = 128, kHintBinShift = 12, kHintHeader = kHintHist + kHintBins };
+struct TileWork {
+    long long batch;
+    unsigned int rows;  // bit r: this warp handles pixel row r of the tile (0xF = the whole tile)
+    unsigned int t0;    // SM clock when the item was fetched
+};
+// s_sched (shared, per block): [0] split entries [1] heavy entries [2] heavy threshold [3] split threshold [4] keep threshold
+// [5] SM clock at block start [6] light entries [7] light threshold
+__device__ __forceinline__ void sched_init(const TraceArgs& a, unsigned int* s_sched) {
+    if (threadIdx.x == 0) {
+        unsigned int n_split = 0, n_heavy = 0, n_light = 0, thr_h = 0xffffffffu, thr_s = 0xffffffffu, thr_k = 0xffffffffu, thr_l = 0u;
+        if (a.hint_in) {
+            n_split = min(a.hint_in[0], (unsigned int)(4 * a.num_batches));
+            n_heavy = min(a.hint_in[1], (unsigned int)a.num_batches);
+            n_light = min(a.hint_in[4], (unsigned int)a.num_batches);
+            const unsigned long long span = a.hint_in[3];
+            const unsigned int tiles = a.hint_in[2];
+            if (span && tiles) {
+                auto pct = [&](int p) { const unsigned long long v = span * (unsigned long long)p / 100ull; return v > 0xfffffffeull ? 0xfffffffeu : (unsigned int)v; };
+                thr_s = pct(a.hint_split_pct);
+                thr_k = pct(a.hint_keep_pct);
+                // heavy = the slowest heavy_pct percent of the timed tiles: walk the histogram down from the top
+                const unsigned long long want = (unsigned long long)tiles * (unsigned long long)a.hint_heavy_pct / 100ull;
+                unsigned long long seen = 0;
+                int bin = kHintBins - 1;
+                for (; bin > 0; bin--) {
+                    seen += a.hint_in[kHintHist + bin];
+                    if (seen >= want) break;
+                }
+                thr_h = (unsigned int)bin << kHintBinShift;
+                if (thr_h > thr_s) thr_h = thr_s;
+                // light = the quickest light_pct percent: walk up from the bottom (bin 0 holds no timed tile)
+                const unsigned long long want_l = (unsigned long long)tiles * (unsigned long long)a.hint_light_pct / 100ull;
+                unsigned long long seen_l = 0;
+                int lb = 1;
+                for (; lb < bin; lb++) {
+                    seen_l += a.hint_in[kHintHist + lb];
+                    if (seen_l > want_l) break;
+                }
+                thr_l = a.hint_light_pct > 0 ? (unsigned int)lb << kHintBinShift : 0u;
+                if (thr_l >= thr_h) thr_l = 0u;
+            }
+        }
+        s_sched[0] = n_split; s_sched[1] = n_heavy; s_sched[2] = thr_h; s_sched[3] = thr_s; s_sched[4] = thr_k;
+        s_sched[5] = (unsigned int)clock();  // the block's warps start together
+        s_sched[6] = n_light; s_sched[7] = thr_l;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ bool next_tile(const TraceArgs& a, const unsigned int* s_sched, int lane, TileWork& tw) {
+    for (;;) {
+        unsigned long long i = 0;
+        if (lane == 0) i = atomicAdd(a.work_counter, 1ull);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        tw.t0 = (unsigned int)clock();
+        const unsigned long long n_split = s_sched[0], n_heavy = s_sched[1];
+        if (i < n_split) {
+            // both lists were appended in completion order, i.e. roughly shortest first: walk them backwards (longest first)
+            const unsigned int e = __ldg(a.hint_in + kHintHeader + (n_split - 1 - i));
+            tw.batch = (long long)(e >> 2);
+            tw.rows = 1u << (e & 3u);
+            if (tw.batch >= a.num_batches) continue;  // cannot happen with a buffer this launch geometry wrote; never trust it
+            return true;
+        }
+        i -= n_split;
+        if (i < n_heavy) {
+            tw.batch = (long long)__ldg(a.hint_in + kHintHeader + 4 * a.num_batches + (n_heavy - 1 - i));
+            tw.rows = 0xFu;
+            if (tw.batch >= a.num_batches) continue;
+            return true;
+        }
+        i -= n_heavy;
+        if (i >= (unsigned long long)a.num_batches) {  // after the main pass: the light tiles, the slowest of them first
+            i -= (unsigned long long)a.num_batches;
+            const unsigned long long n_light = s_sched[6];
+            if (i >= n_light) return false;
+            tw.batch = (long long)__ldg(a.hint_in + kHintHeader + 5 * a.num_batches + (n_light - 1 - i));
+            tw.rows = 0xFu;
+            if (tw.batch >= a.num_batches) continue;
+            return true;
+        }
+        tw.batch = (long long)i;
+        tw.rows = 0xFu;
+        if (a.hint_in) {  // rows that a list entry covers were (or will be) traced by that entry's warp
+            const unsigned int f = __ldg(a.hint_in + kHintHeader + 6 * a.num_batches + i);
+            const unsigned int covered = ((f & 0xffu) ? 1u : 0u) | ((f & 0xff00u) ? 2u : 0u) | ((f & 0xff0000u) ? 4u : 0u) | ((f & 0xff000000u) ? 8u : 0u);
+            tw.rows = 0xFu & ~covered;
+            if (!tw.rows) continue;
+        }
+        return true;
+    }
+}
+// Called by all lanes when the item is done: record the tile's class for the next launch.
+__device__ __forceinline__ void record_tile(const TraceArgs& a, const unsigned int* s_sched, int lane, const TileWork& tw) {
+    if (!a.hint_out || lane != 0) return;
+    const unsigned int dur = (unsigned int)clock() - tw.t0;
+    unsigned char* flags = reinterpret_cast<unsigned char*>(a.hint_out + kHintHeader + 6 * a.num_batches) + 4 * tw.batch;
+    if (tw.rows == 0xFu) {
+        if (dur > 4096u) {  // a tile that traced something (an all-gated tile takes ~2000 cycles): the statistics are over these
+            atomicAdd(a.hint_out + 2, 1u);
+            atomicAdd(a.hint_out + kHintHist + min(dur >> kHintBinShift, (unsigned int)kHintBins - 1u), 1u);
+        }
+        unsigned int word = 0u;
+        if (dur > s_sched[3]) {
+            const unsigned int at = atomicAdd(a.hint_out + 0, 4u);
+            for (unsigned int r = 0; r < 4u; r++) a.hint_out[kHintHeader + at + r] = ((unsigned int)tw.batch << 2) | r;
+            word = 0x01010101u;
+        } else if (dur > s_sched[2]) {
+            const unsigned int at = atomicAdd(a.hint_out + 1, 1u);
+            a.hint_out[kHintHeader + 4 * a.num_batches + at] = (unsigned int)tw.batch;
+            word = 0x01010101u;
+        } else if (dur > 4096u && dur <= s_sched[7]) {
+            const unsigned int at = atomicAdd(a.hint_out + 4, 1u);
+            a.hint_out[kHintHeader + 5 * a.num_batches + at] = (unsigned int)tw.batch;
+            word = 0x01010101u;
+        }
+        *reinterpret_cast<unsigned int*>(flags) = word;
+    } else {  // a single row or the uncovered rows of a tile: rows that are still slow stay on the split list
+        const bool keep = dur > (__popc(tw.rows) == 1 ? s_sched[4] : s_sched[2]);
+        const unsigned int n = keep ? __popc(tw.rows) : 0u;
+        unsigned int at = n ? atomicAdd(a.hint_out + 0, n) : 0u;
+        for (unsigned int r = 0; r < 4u; r++)
+            if (tw.rows & (1u << r)) {
+                flags[r] = keep ? 1 : 0;
+                if (keep) a.hint_out[kHintHeader + at++] = ((unsigned int)tw.batch << 2) | r;
+            }
+    }
+}
+// Called once per warp when it retires: the launch span is the longest life of a persistent warp.
+__device__ __forceinline__ void record_span(const TraceArgs& a, const unsigned int* s_sched, int lane) {
+    if (a.hint_out && lane == 0) atomicMax(a.hint_out + 3, (unsigned int)clock() - s_sched[5]);
+}
+
 __device__ __forceinline__ void store_ray(float4* rays_out, long long i, const Ray& r) {
     rays_out[2 * i] = make_float4(r.ori.x, r.ori.y, r.ori.z, RTB_T_INIT);
     rays_out[2 * i + 1] = make_float4(r.dir.x, r.dir.y, r.dir.z, 0.0f);
@@ -210,7 +375,7 @@ __device__ __forceinline__ void store_ray(float4* rays_out, long long i, const R
 // Grid = (resident blocks per SM) x 148 SMs; every warp pulls 32-ray batches from a global queue
 // head with one atomicAdd by lane 0 + a shuffle, until the queue is empty.
 template <int SRC, bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX = false>
-__global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(const TraceArgs a, int smem_count) {
+__global__ void __launch_bounds__(kBlockThreads, (SRC == SRC_PRIMARY && !FAST_BOX) ? 8 : RTB_MINB_BATCH) trace_kernel(const TraceArgs a, int smem_count) {
     extern __shared__ float4 smem_pairs[];
     if (SMEM_TOP) {
         for (int i = threadIdx.x; i < smem_count * 4; i += blockDim.x) smem_pairs[i] = a.scene.pairs[i];
@@ -218,11 +383,19 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
     }
     const int lane = threadIdx.x & 31;
     unsigned int traced = 0;
+    __shared__ unsigned int s_sched[8];
+    if (SRC == SRC_PRIMARY) sched_init(a, s_sched);
     for (;;) {
         unsigned long long batch = 0;
-        if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
-        batch = __shfl_sync(0xffffffffu, batch, 0);
-        if (batch >= (unsigned long long)a.num_batches) break;
+        TileWork tw;
+        if (SRC == SRC_PRIMARY) {
+            if (!next_tile(a, s_sched, lane, tw)) break;
+            batch = (unsigned long long)tw.batch;
+        } else {
+            if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
+            batch = __shfl_sync(0xffffffffu, batch, 0);
+            if (batch >= (unsigned long long)a.num_batches) break;
+        }
         RTB_TL_BEGIN(a);
 
         Ray ray;
@@ -245,7 +418,7 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
             int x, y;
             tile_pixel(a, (long long)batch, lane, x, y, tile_x, tile_k);
             tile_y0 = y - (lane >> 3);
-            if (x < a.w && y < a.h) {
+            if (x < a.w && y < a.h && ((tw.rows >> (lane >> 3)) & 1u)) {
                 out_index = (long long)y * a.w + x;
                 if (a.rays_out || !certainly_gated_out(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h))
                     active = primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray);
@@ -284,9 +457,14 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_BATCH) trace_kernel(co
             if (SRC != SRC_PRIMARY || a.hits_out) a.hits_out[out_index] = make_float4(__int_as_float(r.idx), r.t, r.u, r.v);
             if (SRC == SRC_PRIMARY && a.frame_out) pixel_sink(a)[out_index] = (unsigned int)r.idx;
         }
-        if (SRC == SRC_PRIMARY && a.frame_out) finish_tile(a, tile_x, tile_k, tile_y0, lane);
+        if (SRC == SRC_PRIMARY) {
+            if (a.frame_out) finish_tile(a, tile_x, tile_k, tile_y0, lane, __popc(tw.rows));
+            __syncwarp();
+            record_tile(a, s_sched, lane, tw);
+        }
         RTB_TL_END(a, batch, lane);
     }
+    if (SRC == SRC_PRIMARY) record_span(a, s_sched, lane);
     retire_ray_count(a, traced, lane);
 }
 
@@ -301,16 +479,17 @@ __global__ void __launch_bounds__(kBlockThreads) primary_shadow_kernel(const Tra
     const int lane = threadIdx.x & 31;
     const f3 light_pos = ld3(a.params.light_pos);
     unsigned int traced = 0;
+    __shared__ unsigned int s_sched[8];
+    sched_init(a, s_sched);
     for (;;) {
-        unsigned long long batch = 0;
-        if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
-        batch = __shfl_sync(0xffffffffu, batch, 0);
-        if (batch >= (unsigned long long)a.num_batches) break;
+        TileWork tw;
+        if (!next_tile(a, s_sched, lane, tw)) break;
+        const long long batch = tw.batch;
         RTB_TL_BEGIN(a);
         int x, y, tx;
         long long k;
-        tile_pixel(a, (long long)batch, lane, x, y, tx, k);
-        if (x < a.w && y < a.h) {
+        tile_pixel(a, batch, lane, x, y, tx, k);
+        if (x < a.w && y < a.h && ((tw.rows >> (lane >> 3)) & 1u)) {
             const long long px = (long long)y * a.w + x;
             Ray ray;
             TraceResult hit;
@@ -331,9 +510,12 @@ __global__ void __launch_bounds__(kBlockThreads) primary_shadow_kernel(const Tra
             if (a.shadow_hits_out) a.shadow_hits_out[px] = make_float4(__int_as_float(sh.idx), sh.t, sh.u, sh.v);
             if (a.frame_out) pixel_sink(a)[px] = hit.idx < 0 ? 0xffffffffu : (unsigned int)(hit.idx + ((sh.idx >= 0 && sh.t > 0.025f) ? 1 : 0));
         }
-        if (a.frame_out) finish_tile(a, tx, k, y - (lane >> 3), lane);
+        if (a.frame_out) finish_tile(a, tx, k, y - (lane >> 3), lane, __popc(tw.rows));
+        __syncwarp();
+        record_tile(a, s_sched, lane, tw);
         RTB_TL_END(a, batch, lane);
     }
+    record_span(a, s_sched, lane);
     retire_ray_count(a, traced, lane);
 }
 
@@ -489,18 +671,24 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_kernel(const TraceArg
     }
     const int lane = threadIdx.x & 31;
     unsigned int traced = 0;
+    __shared__ unsigned int s_sched[8];
+    sched_init(a, s_sched);
     for (;;) {
-        unsigned long long batch = 0;
-        if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
-        batch = __shfl_sync(0xffffffffu, batch, 0);
-        if (batch >= (unsigned long long)a.num_batches) break;
+        TileWork tw;
+        if (!next_tile(a, s_sched, lane, tw)) break;
+        const long long batch = tw.batch;
+        RTB_TL_BEGIN(a);
         int x, y, tx;
         long long k;
-        tile_pixel(a, (long long)batch, lane, x, y, tx, k);
-        if (x < a.w && y < a.h)
+        tile_pixel(a, batch, lane, x, y, tx, k);
+        if (x < a.w && y < a.h && ((tw.rows >> (lane >> 3)) & 1u))
             pixel_sink(a)[(size_t)y * a.w + x] = render_pixel<SMEM_TOP>(a, smem_pairs, smem_count, (unsigned)x, (unsigned)y, traced);
-        finish_tile(a, tx, k, y - (lane >> 3), lane);
+        finish_tile(a, tx, k, y - (lane >> 3), lane, __popc(tw.rows));
+        __syncwarp();
+        record_tile(a, s_sched, lane, tw);
+        RTB_TL_END(a, batch, lane);
     }
+    record_span(a, s_sched, lane);
     retire_ray_count(a, traced, lane);
 }
 

@@ -78,6 +78,22 @@ struct rt_context {
     int opt_overlap_frames = 1; // rt_render_frame_begin: one-kernel frames on per-slot streams (frames in flight overlap)
     int opt_store_group = -1;   // row assembly of 4-byte/pixel frames: -1 = auto (on when the frame is host or peer memory),
                                 // 0 = off, 2 = groups of 4 tiles (128-byte rows), 4 = groups of 16 tiles (512-byte rows)
+    int opt_tile_hints = 1;     // temporal tile scheduling of the camera-ray kernels (kernels.cuh "tile scheduler")
+    int opt_hint_heavy_pct = 12;                        // the slowest N percent of the tiles start first
+    int opt_hint_light_pct = 35;                        // the quickest N percent run last
+    int opt_hint_split_pct = 80, opt_hint_keep_pct = 30;  // percent of the previous launch's span: split a tile / keep a row split
+    // What a launch learnt about its tiles, kept per frame geometry for the next launch of the same geometry. Two buffers
+    // per slot: launch k reads the one launch k-1 wrote and writes the other.
+    struct HintSlot {
+        int kind = -1, w = 0, h = 0, part = 0, n_parts = 0, band_tile_rows = 0, frame_slot = -2;
+        long long num_batches = 0;
+        unsigned int* buf[2] = {nullptr, nullptr};
+        size_t bytes = 0;
+        int cur = 0;          // buf[cur] = written by the last launch
+        bool valid = false;   // buf[cur] holds hints
+        uint64_t last_use = 0;
+    } hint_slots[16];
+    uint64_t hint_clock = 0;
     uint64_t counters[RT_CNT_COUNT] = {0};
 #ifdef RTB_TIMELINE
     unsigned long long* d_timeline = nullptr;  // tools build only (see kernels.cuh)
@@ -175,7 +191,13 @@ extern "C" int rt_create(int device_ordinal, rt_context** out_ctx) {
     return RT_OK;
 }
 
+// Hints describe a frame of the scene that was current when they were recorded: a new scene or new thresholds start over.
+static void forget_hints(rt_context* ctx) {
+    for (auto& hs : ctx->hint_slots) hs.valid = false;
+}
+
 static void free_scene(rt_context* ctx) {
+    forget_hints(ctx);
     if (ctx->d_blob && ctx->blob_owned) cudaFree(ctx->d_blob);
     ctx->d_blob = nullptr;
     ctx->blob_bytes = 0;
@@ -208,6 +230,10 @@ extern "C" int rt_destroy(rt_context* ctx) {
     }
     cudaFree(ctx->rowasm.stage);
     cudaFree(ctx->rowasm.counts);
+    for (auto& hs : ctx->hint_slots) {
+        cudaFree(hs.buf[0]);
+        cudaFree(hs.buf[1]);
+    }
     cudaFree(ctx->d_sort);
     if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -349,8 +375,35 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
         if (ctx->have_scene) ctx->view.coords_in_window = ctx->opt_exact_div ? 0 : ctx->hdr.coords_in_window;
     } else if (!strcmp(name, "overlap_frames")) ctx->opt_overlap_frames = value ? 1 : 0;
     else if (!strcmp(name, "store_group")) ctx->opt_store_group = (value == 0 || value == 2 || value == 4) ? value : -1;
+    else if (!strcmp(name, "tile_hints")) { ctx->opt_tile_hints = value ? 1 : 0; forget_hints(ctx); }
+    else if (!strcmp(name, "hint_heavy_pct")) { ctx->opt_hint_heavy_pct = value < 1 ? 1 : value; forget_hints(ctx); }
+    else if (!strcmp(name, "hint_light_pct")) { ctx->opt_hint_light_pct = value < 0 ? 0 : (value > 90 ? 90 : value); forget_hints(ctx); }
+    else if (!strcmp(name, "hint_split_pct")) { ctx->opt_hint_split_pct = value < 1 ? 1 : value; forget_hints(ctx); }
+    else if (!strcmp(name, "hint_keep_pct")) { ctx->opt_hint_keep_pct = value < 1 ? 1 : value; forget_hints(ctx); }
     else if (!strcmp(name, "top_pairs")) ctx->opt_top_pairs = value < 0 ? 0 : value;  // takes effect at the next upload
     else return set_err(ctx, RT_E_INVALID, "rt_set_option: unknown option '%s'", name);
+    return RT_OK;
+}
+
+// What the most recent camera-ray launch recorded for its successor: [0] one-row entries on the split list, [1] tiles on the
+// heavy list, [2] tiles timed, [3] the launch span in SM clock cycles. All zero when tile hints are off / nothing ran yet.
+extern "C" int rt_tile_hint_stats(rt_context* ctx, uint64_t out[4]) {
+    if (!ctx || !out) return RT_E_INVALID;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    const rt_context::HintSlot* last = nullptr;
+    for (const auto& hs : ctx->hint_slots)
+        if (hs.valid && (!last || hs.last_use > last->last_use)) last = &hs;
+    if (!last) return RT_OK;
+    ON_DEVICE(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& sl : ctx->slots)
+        if (sl.pending) CK(ctx, cudaEventSynchronize(sl.done));
+    unsigned int hdr[16];
+    CK(ctx, cudaMemcpy(hdr, last->buf[last->cur], sizeof hdr, cudaMemcpyDeviceToHost));
+    out[0] = hdr[0];
+    out[1] = hdr[1];
+    out[2] = hdr[2];
+    out[3] = hdr[3];
     return RT_OK;
 }
 
@@ -450,6 +503,78 @@ template <typename K>
 static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, int smem_count, cudaStream_t stream = nullptr,
                              unsigned long long* counter = nullptr, size_t zero_bytes = sizeof(unsigned long long)) {
     return launch_persistent(ctx, kernel, a, (size_t)smem_count * 64, stream, counter, zero_bytes, smem_count);
+}
+
+// ---- temporal tile scheduling: hint slots (device side: kernels.cuh "tile scheduler") -----------------------------------
+enum { HINT_KIND_PRIMARY = 0, HINT_KIND_PRIMARY_SHADOW = 1, HINT_KIND_FRAME = 2 };
+// Bind the hint buffers of this launch's frame geometry to `a`: hint_in = what the previous launch of the same geometry
+// (same kernel kind, frame size, band partition and frame slot) recorded, hint_out = where this launch records. Frames in
+// flight on different frame slots have their own slots, so two launches never share a buffer.
+static int attach_hints(rt_context* ctx, int kind, TraceArgs& a, int frame_slot, cudaStream_t stream, rt_context::HintSlot** out_slot) {
+    *out_slot = nullptr;
+    a.hint_in = nullptr;
+    a.hint_out = nullptr;
+    a.hint_heavy_pct = ctx->opt_hint_heavy_pct;
+    a.hint_light_pct = ctx->opt_hint_light_pct;
+    a.hint_split_pct = ctx->opt_hint_split_pct;
+    a.hint_keep_pct = ctx->opt_hint_keep_pct;
+    if (!ctx->opt_tile_hints || a.tile_order != 0 || a.num_batches < 1 || a.num_batches > (1ll << 29)) return RT_OK;
+    // A pass that stores straight into host memory is paced by the PCIe link, which wants the stores spread evenly over
+    // the launch; starting the slow tiles first and ending on the quick ones bunches the stores at the end (measured:
+    // rt_primary into pinned memory 0.71 -> 0.78 ms). Such passes keep the plain row-major queue.
+    auto in_host_memory = [](const void* p) {
+        if (!p) return false;
+        cudaPointerAttributes attr;
+        memset(&attr, 0, sizeof attr);
+        if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return attr.type == cudaMemoryTypeHost;
+    };
+    if (in_host_memory(a.frame_out) || in_host_memory(a.hits_out) || in_host_memory(a.shadow_hits_out)) return RT_OK;
+    rt_context::HintSlot* hs = nullptr;
+    rt_context::HintSlot* lru = &ctx->hint_slots[0];
+    for (auto& c : ctx->hint_slots) {
+        if (c.kind == kind && c.w == a.w && c.h == a.h && c.part == a.part && c.n_parts == a.n_parts && c.band_tile_rows == a.band_tile_rows &&
+            c.frame_slot == frame_slot && c.num_batches == a.num_batches) {
+            hs = &c;
+            break;
+        }
+        if (c.last_use < lru->last_use) lru = &c;
+    }
+    const size_t bytes = sizeof(unsigned int) * ((size_t)kHintHeader + 7 * (size_t)a.num_batches);
+    if (!hs) {  // a geometry not seen lately: take over the least recently used slot
+        hs = lru;
+        if (hs->bytes < bytes) {
+            cudaFree(hs->buf[0]);  // (synchronises with launches that may still read them)
+            cudaFree(hs->buf[1]);
+            hs->buf[0] = hs->buf[1] = nullptr;
+            hs->bytes = 0;
+            CK(ctx, cudaMalloc((void**)&hs->buf[0], bytes));
+            CK(ctx, cudaMalloc((void**)&hs->buf[1], bytes));
+            hs->bytes = bytes;
+        }
+        hs->kind = kind; hs->w = a.w; hs->h = a.h; hs->part = a.part; hs->n_parts = a.n_parts; hs->band_tile_rows = a.band_tile_rows;
+        hs->frame_slot = frame_slot; hs->num_batches = a.num_batches;
+        hs->cur = 0;
+        hs->valid = false;
+    }
+    hs->last_use = ++ctx->hint_clock;
+    a.hint_in = hs->valid ? hs->buf[hs->cur] : nullptr;
+    a.hint_out = hs->buf[hs->cur ^ 1];
+    CK(ctx, cudaMemsetAsync(a.hint_out, 0, kHintHeader * sizeof(unsigned int), stream ? stream : ctx->stream));  // list counts + time sums
+    *out_slot = hs;
+    return RT_OK;
+}
+static void commit_hints(rt_context::HintSlot* hs, int rc) {
+    if (!hs) return;
+    if (rc == RT_OK) {
+        hs->cur ^= 1;
+        hs->valid = true;
+    } else {
+        hs->valid = false;
+    }
 }
 
 // Destination of a pass's 4-byte/pixel frame. Decides whether rows are assembled (TraceArgs::stage): always when the
@@ -710,12 +835,15 @@ static int primary_impl(rt_context* ctx, int w, int h, int part, int n_parts, in
     if ((rc = frame_sink(ctx, a, d_idx_frame, ctx->rowasm, &counter, &zero_bytes))) return rc;
     const int st = smem_top_count(ctx);
     if (ctx->opt_scheduler == 1 && !st && d_hits && !d_idx_frame)
-        rc = launch_lanes(ctx, trace_lanes_kernel<SRC_PRIMARY, false>, a, a.num_batches * 32);
-    else if (ctx->opt_fast_box && !st)
+        return launch_lanes(ctx, trace_lanes_kernel<SRC_PRIMARY, false>, a, a.num_batches * 32);
+    rt_context::HintSlot* hs = nullptr;
+    if ((rc = attach_hints(ctx, HINT_KIND_PRIMARY, a, -1, nullptr, &hs))) return rc;
+    if (ctx->opt_fast_box && !st)
         rc = launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false, true>, a, 0, nullptr, counter, zero_bytes);
     else
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, true>, a, st, nullptr, counter, zero_bytes)
                 : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0, nullptr, counter, zero_bytes);
+    commit_hints(hs, rc);
     return rc;
 }
 
@@ -736,7 +864,11 @@ static int primary_shadow_impl(rt_context* ctx, int w, int h, int part, int n_pa
     unsigned long long* counter = nullptr;
     size_t zero_bytes = 0;
     if ((rc = frame_sink(ctx, a, d_vis_frame, ctx->rowasm, &counter, &zero_bytes))) return rc;
-    return launch_persistent(ctx, primary_shadow_kernel, a, (size_t)0, nullptr, counter, zero_bytes);
+    rt_context::HintSlot* hs = nullptr;
+    if ((rc = attach_hints(ctx, HINT_KIND_PRIMARY_SHADOW, a, -1, nullptr, &hs))) return rc;
+    rc = launch_persistent(ctx, primary_shadow_kernel, a, (size_t)0, nullptr, counter, zero_bytes);
+    commit_hints(hs, rc);
+    return rc;
 }
 
 extern "C" int rt_primary_shadow_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, rt_hit* d_hits,
@@ -969,8 +1101,12 @@ static int render_frame_impl(rt_context* ctx, int w, int h, int part, int n_part
     size_t zero_bytes = sizeof(unsigned long long);
     if ((rc = frame_sink(ctx, a, d_out, slot >= 0 ? ctx->slots[slot].rowasm : ctx->rowasm, &counter, &zero_bytes))) return rc;
     const int st = smem_top_count(ctx);
-    return st ? launch_persistent(ctx, render_kernel<true>, a, st, stream, counter, zero_bytes)
-              : launch_persistent(ctx, render_kernel<false>, a, 0, stream, counter, zero_bytes);
+    rt_context::HintSlot* hs = nullptr;
+    if ((rc = attach_hints(ctx, HINT_KIND_FRAME, a, slot, stream, &hs))) return rc;
+    rc = st ? launch_persistent(ctx, render_kernel<true>, a, st, stream, counter, zero_bytes)
+            : launch_persistent(ctx, render_kernel<false>, a, 0, stream, counter, zero_bytes);
+    commit_hints(hs, rc);
+    return rc;
 }
 
 extern "C" int rt_render_frame_device(rt_context* ctx, int w, int h, int part, int n_parts, int band_rows, uint32_t* d_out) {

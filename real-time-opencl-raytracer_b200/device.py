@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "rt_memcpy_to_host", "rt_host_register", "rt_host_unregister", "rt_signal", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
     "rt_create_group", "rt_destroy_group", "rt_group_last_error", "rt_group_size", "rt_group_context", "rt_group_upload_scene",
     "rt_group_set_params", "rt_group_set_option", "rt_render_frame_tiled", "rt_primary_tiled", "rt_group_stats",
-    "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest", "rt_selftest_range", "rt_selftest_exhaustive", "rt_pack_scene_host", "rt_free_host",
+    "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest", "rt_selftest_range", "rt_selftest_exhaustive", "rt_tile_hint_stats", "rt_pack_scene_host", "rt_free_host",
 ]
 
 
@@ -83,6 +83,7 @@ def lib():
         L.rt_free_host.argtypes = [vp]
         L.rt_free_host.restype = None
         L.rt_selftest_range.argtypes = [vp, i64, C.c_uint32, i32, C.POINTER(C.c_uint64)]
+        L.rt_tile_hint_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.rt_selftest_exhaustive.argtypes = [vp, C.c_uint32, C.c_uint32, i32, i32, C.c_uint32, C.POINTER(C.c_uint64)]
         L.rt_create_group.argtypes = [i32, vp, C.POINTER(vp)]
         L.rt_destroy_group.argtypes = [vp]
@@ -288,6 +289,11 @@ class Context:
         bad = C.c_uint64(0)
         self._ck(lib().rt_selftest_range(self._h, samples, seed, x_exponent, C.byref(bad)))
         return int(bad.value)
+
+    def tile_hint_stats(self):
+        out = (C.c_uint64 * 4)()
+        self._ck(lib().rt_tile_hint_stats(self._h, out))
+        return {"split_rows": int(out[0]), "heavy_tiles": int(out[1]), "tiles_timed": int(out[2]), "span_cycles": int(out[3])}
 
     def selftest_exhaustive(self, md_begin, md_count, ex_x=0, ex_d=0, signs=0):
         """all 2^23 numerator mantissas x md_count divisor mantissas: mismatches of the hoisted division vs `/`"""

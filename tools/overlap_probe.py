@@ -26,7 +26,9 @@ def run(slots, consume):
     for k in range(nf - (slots - 1), nf):
         ctx.render_frame_end(k % slots)
     return (time.perf_counter() - t0) / nf * 1e3
-for rnd in range(3):
+for rnd in range(2):
+  for sg in (-1, 0, 2):
+    ctx.set_option("store_group", sg)
     for ov in (0, 1):
         ctx.set_option("overlap_frames", ov)
-        print(f"overlap_frames={ov}: " + "  ".join(f"slots={s} consume={c}: {run(s, c):.3f} ms/frame" for s in (1, 2, 3) for c in (False, True)), flush=True)
+        print(f"store_group={sg} overlap_frames={ov}: " + "  ".join(f"slots={s} consume={c}: {run(s, c):.3f} ms/frame" for s in (1, 2, 3) for c in (False, True)), flush=True)

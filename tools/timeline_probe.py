@@ -20,6 +20,7 @@ from rtb200 import device as D
 out_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/timeline_probe.json"
 W, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (3840, 2160)
 RAW_DIR = sys.argv[4] if len(sys.argv) > 4 else None  # also dump the raw per-tile stamps there
+PARTS = tuple(int(v) for v in os.environ.get("RTB_PROBE_PARTS", "1,2,4,8").split(","))
 rtb200.hostlib.set_num_threads(os.cpu_count() or 1)
 mesh = rtb200.Mesh().terrain(707, 100.0).finish()
 A = mesh.arrays()
@@ -30,6 +31,9 @@ stream = torch.cuda.Stream()
 ctx.set_stream(stream.cuda_stream)
 ctx.upload_scene(A, bvh.nodes, bvh.tri_indices)
 ctx.set_params(params)
+for opt in ("tile_hints", "hint_heavy_pct", "hint_light_pct", "hint_split_pct", "hint_keep_pct"):  # A/B from the environment, e.g. RTB_TILE_HINTS=0
+    if ("RTB_" + opt.upper()) in os.environ:
+        ctx.set_option(opt, int(os.environ["RTB_" + opt.upper()]))
 L = D.lib()
 have_tl = hasattr(L, "rt_debug_timeline")
 if have_tl:
@@ -80,7 +84,7 @@ def timeline(kind, part, n_parts, band_rows=16, do_flush=True):
     nb = n_batches(part, n_parts, band_rows)
     buf = torch.zeros((nb, 2), dtype=torch.int64, device="cuda")
     with torch.cuda.stream(stream):
-        for _ in range(2):
+        for _ in range(4):  # the tile hints settle after two launches of a geometry
             launch(kind, part, n_parts, band_rows)
     torch.cuda.synchronize()
     if do_flush:
@@ -128,17 +132,21 @@ def timeline(kind, part, n_parts, band_rows=16, do_flush=True):
 res = {"frame": [W, H], "scene": "C2 terrain (999 698 triangles), default camera + light", "timeline_build": bool(have_tl)}
 for kind in ("primary_shadow", "primary", "shaded_frame"):
     r = {}
-    for n_parts in (1, 2, 4, 8):
+    for n_parts in PARTS:
         per_part = [timed(lambda p=p: launch(kind, p, n_parts)) for p in range(n_parts)]
         r[f"n{n_parts}"] = {"max_ms": max(per_part), "mean_ms": float(np.mean(per_part)), "per_part_ms": per_part}
-    r["n8_no_flush_ms"] = max(timed(lambda p=p: launch(kind, p, 8), do_flush=False) for p in range(8))
-    for n_parts in (1, 8):
+    if 8 in PARTS:
+        r["n8_no_flush_ms"] = max(timed(lambda p=p: launch(kind, p, 8), do_flush=False) for p in range(8))
+    for n_parts in PARTS:
         r[f"speedup_n{n_parts}"] = r["n1"]["max_ms"] / r[f"n{n_parts}"]["max_ms"]
     if have_tl:
         r["timeline_n8_part3"] = timeline(kind, 3, 8)
         r["timeline_n1"] = timeline(kind, 0, 1)
+    launch(kind, 3, 8)
+    r["hint_stats_n8_part3"] = ctx.tile_hint_stats()
     res[kind] = r
-    print(kind, json.dumps({k: v for k, v in r.items() if not k.startswith("timeline")}), flush=True)
+    print(kind, json.dumps({k: (v if not isinstance(v, dict) or "per_part_ms" not in v else {"max_ms": v["max_ms"], "mean_ms": v["mean_ms"]})
+                            for k, v in r.items() if not k.startswith("timeline")}), flush=True)
     if have_tl:
         for k in ("timeline_n8_part3", "timeline_n1"):
             if r[k]:
