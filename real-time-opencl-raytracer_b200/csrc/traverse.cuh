@@ -90,6 +90,13 @@ __device__ __forceinline__ TraceResult traverse_impl(const SceneView& s, const f
                 if (sp >= RTB_STACK) { res.idx = -1; res.t = tHit; res.u = res.v = 0.0f; return res; }
                 stack[sp++] = c1;
                 cur = c0;
+#ifdef RTB_PREFETCH_FAR
+                // experiment: the postponed child will be popped later -- pull its node pair / first triangle towards L2 now
+                if (c1 != kRefPoison) {
+                    const void* pf = c1 >= 0 ? (const void*)(s.pairs + 4 * (size_t)c1) : (const void*)(s.tris + 3 * (size_t)(~c1));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                }
+#endif
             } else if (hit0) {
                 cur = c0;
             } else if (hit1) {
@@ -103,6 +110,28 @@ __device__ __forceinline__ TraceResult traverse_impl(const SceneView& s, const f
         if (cur == kRefPoison) { res.idx = -1; res.t = tHit; res.u = res.v = 0.0f; return res; }
         {
             const float4* tp = s.tris + 3 * (size_t)(~cur);
+#ifdef RTB_LEAF_PIPE
+            // experiment: the next triangle of the leaf is loaded before the current one is tested (the loop's exit
+            // depends on the current triangle's `last` flag, so the hardware cannot start that load on its own)
+            float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            for (;;) {
+                const bool last = __float_as_int(b.w) != 0;
+                float4 na = a, nb = b, nc = c;
+                if (!last) { na = __ldg(tp + 3); nb = __ldg(tp + 4); nc = __ldg(tp + 5); }
+                float u, v;
+                const float t = ray_triangle(ray, ld3(a), ld3(b), ld3(c), u, v);
+                if (t < tHit && t > RTB_TMIN) {
+                    tHit = t;
+                    res.idx = __float_as_int(a.w);
+                    res.u = u;
+                    res.v = v;
+                    if (ANY_HIT) { res.t = tHit; return res; }
+                }
+                if (last) break;
+                a = na; b = nb; c = nc;
+                tp += 3;
+            }
+#else
             for (;;) {
                 const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                 float u, v;
@@ -117,6 +146,7 @@ __device__ __forceinline__ TraceResult traverse_impl(const SceneView& s, const f
                 if (__float_as_int(b.w) != 0) break;
                 tp += 3;
             }
+#endif
         }
         if (sp == 0) { res.t = tHit; return res; }
         cur = stack[--sp];
