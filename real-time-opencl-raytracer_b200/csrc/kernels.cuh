@@ -871,6 +871,32 @@ __global__ void selftest_division_exhaustive_kernel(unsigned int md0, int ex_x, 
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, (unsigned long long)bad);
 }
 
+// ---- validation of an adopted blob (rt_adopt_scene_blob) --------------------------------------------------------------
+// A blob uploaded by rt_upload_scene was validated on the host before packing; one that arrives in device memory (NCCL
+// broadcast, peer copy) is checked here once: every child reference of every node pair points inside the pair / triangle
+// sections, every packed triangle's id indexes the shading arrays, and the sentinel behind the last triangle terminates
+// any leaf run -- so a stale or corrupt buffer is rejected instead of read out of bounds or looped over forever.
+__global__ void validate_blob_kernel(const float4* pairs, int num_pairs, const float4* tris, int num_tris, int T, int root_ref,
+                                     unsigned int* bad) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned int wrong = 0;
+    auto ref_ok = [&](int ref) {
+        if (ref == kRefPoison) return true;
+        return ref >= 0 ? ref < num_pairs : ~ref <= num_tris;
+    };
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < num_pairs; i += stride) {
+        wrong += !ref_ok(__float_as_int(pairs[4 * i + 1].z));
+        wrong += !ref_ok(__float_as_int(pairs[4 * i + 3].z));
+    }
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j <= num_tris; j += stride) {
+        const int id = __float_as_int(tris[3 * j].w), last = __float_as_int(tris[3 * j + 1].w);
+        if (j == num_tris) wrong += (last == 0);  // the sentinel ends every leaf run
+        else wrong += (id < 0 || id % 3 != 0 || (T > 0 && id / 3 >= T) || (last != 0 && last != 1));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) wrong += !ref_ok(root_ref);
+    if (wrong) atomicAdd(bad, wrong);
+}
+
 // ---- SASS probes (tests/test_sass.py reads them with cuobjdump; they are never launched) ---------------------------
 // probe_ray_triangle_kernel holds exactly one inlined ray_triangle(); probe_reciprocal_kernel exactly one IEEE 1.0f / x.
 // If ptxas contracted any product-sum of Moller-Trumbore into an FFMA, the first kernel would show more FFMAs than the

@@ -353,7 +353,22 @@ extern "C" int rt_adopt_scene_blob(rt_context* ctx, void* device_ptr, size_t byt
     BlobHeader h;
     CK(ctx, cudaMemcpyAsync(&h, device_ptr, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    return bind_blob(ctx, h, (uint8_t*)device_ptr, bytes, false);
+    int rc = bind_blob(ctx, h, (uint8_t*)device_ptr, bytes, false);
+    if (rc) return rc;
+    // the header is consistent; now the contents it describes (see validate_blob_kernel)
+    unsigned int* d_bad = (unsigned int*)(ctx->d_counter + 9);
+    CK(ctx, cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), ctx->stream));
+    validate_blob_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->view.pairs, h.num_pairs, ctx->view.tris, h.num_tris, h.Vn && h.M ? h.T : 0,
+                                                                    h.root_ref, d_bad);
+    CK(ctx, cudaGetLastError());
+    unsigned int bad = 0;
+    CK(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad) {
+        free_scene(ctx);
+        return set_err(ctx, RT_E_INVALID, "scene blob rejected: %u child references / triangle records point outside their sections", bad);
+    }
+    return RT_OK;
 }
 
 extern "C" int rt_set_params(rt_context* ctx, const float params[32]) {

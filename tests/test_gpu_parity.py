@@ -505,6 +505,20 @@ def test_scene_blob_adopt_roundtrip(ctx):
         bad[:256] = torch.from_numpy(h2).cuda()
         with pytest.raises(rtb200.RtError, match="rejected|mismatch"):
             c2.adopt_scene_blob(bad.data_ptr(), nbytes)
+    # ... and so are CONTENTS that point outside their sections: a child reference past the pair section, a
+    # triangle id past the mesh, a missing leaf terminator on the sentinel -- checked by one kernel when a blob is adopted
+    off_pairs = int(np.frombuffer(hdr[64:72].tobytes(), dtype=np.uint64)[0])
+    off_tris = int(np.frombuffer(hdr[72:80].tobytes(), dtype=np.uint64)[0])
+    num_tris = int(np.frombuffer(hdr[24:28].tobytes(), dtype=np.int32)[0])
+    for byte_at, value in ((off_pairs + 16 + 8, 2**30),                    # pair 0, child 0 reference
+                           (off_pairs + 64 * 3 + 48 + 8, -(2**30)),         # pair 3, child 1: leaf reference far past the triangles
+                           (off_tris + 48 * 2 + 12, 3 * 10**8),             # triangle 2: id beyond the mesh
+                           (off_tris + 48 * num_tris + 16 + 12, 0)):        # the sentinel's `last` flag
+        bad = moved.clone()
+        bad[byte_at:byte_at + 4] = torch.from_numpy(np.frombuffer(np.int32(value).tobytes(), dtype=np.uint8).copy()).cuda()
+        with pytest.raises(rtb200.RtError, match="rejected"):
+            c2.adopt_scene_blob(bad.data_ptr(), nbytes)
+    c2.adopt_scene_blob(moved.data_ptr(), nbytes)  # the intact copy is still accepted afterwards
     with pytest.raises(rtb200.RtError):
         c2.adopt_scene_blob(moved.data_ptr(), nbytes - 256)
     shifted = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")

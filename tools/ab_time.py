@@ -17,7 +17,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     w, h = 1920, 1080
     mesh = rtb200.Mesh().terrain(707, 100.0).finish(diffuse=(0.7, 0.7, 0.7))
     A = mesh.arrays()
-    cache = os.path.join(ROOT, "gpurun_out", "ab_bvh.bin")
+    cache = "/tmp/rtb200_ab_bvh.bin"
     bvh = rtb200.FlatBVH.load(cache) if os.path.exists(cache) else rtb200.FlatBVH.build(mesh)
     if not os.path.exists(cache):
         bvh.save(cache)

@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import rtb200
 w, h = 1920, 1080
 mesh = rtb200.Mesh().terrain(707, 100.0).finish(diffuse=(0.7, 0.7, 0.7)); A = mesh.arrays()
-cache = os.path.join(ROOT, "gpurun_out", "ab_bvh.bin")
+cache = "/tmp/rtb200_ab_bvh.bin"
 bvh = rtb200.FlatBVH.load(cache) if os.path.exists(cache) else rtb200.FlatBVH.build(mesh)
 params, _ = rtb200.camera_params(w, h, A["aabb_min"], A["aabb_max"])
 ctx = rtb200.Context(0); ctx.upload_scene(A, bvh.nodes, bvh.tri_indices); ctx.set_params(params)

@@ -34,12 +34,11 @@ else:
     mesh = rtb200.Mesh().sphere_field(11, 120.0, 6, 50.0).finish(diffuse=(0.7, 0.7, 0.7))
     d_radius = 1320.0
 A = mesh.arrays()
-cache = os.path.join(ROOT, "gpurun_out", f"prof_{scene}.fbvh")
+cache = f"/tmp/rtb200_prof_{scene}.fbvh"  # on the GPU box, NOT under gpurun_out/ (64 MiB limit for what travels back)
 if os.path.exists(cache):
     bvh = rtb200.FlatBVH.load(cache)
 else:
     bvh = rtb200.FlatBVH.build(mesh)
-    os.makedirs(os.path.dirname(cache), exist_ok=True)
     bvh.save(cache)
 params, _ = rtb200.camera_params(w, h, A["aabb_min"], A["aabb_max"], d_radius=d_radius)
 ctx = rtb200.Context(0)
