@@ -227,7 +227,7 @@ def roofline_of(cnt, io_bytes, ms, kernel, resident, capture=None):
     algo = 64 * cnt["inner"] + 48 * cnt["tris"] + io_bytes
     achieved = algo / (ms * 1e-3) / 1e9
     cap = load_capture(capture) if capture else {}
-    return {"bound": "l2-resident (latency)" if resident else "hbm",
+    return {"bound": "l2-resident (latency)" if resident else "hbm-resident scene (L2-miss latency + divergence; DRAM bandwidth 7-12 % of peak)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": cap.get("dram_bytes_per_launch"), "l2_bytes_per_launch": cap.get("l2_bytes_per_launch"),
             "l1_bytes_per_launch": cap.get("l1_bytes_per_launch"), "capture": cap.get("source"),
@@ -452,7 +452,7 @@ def main():
         host_frame = None
         if not args.nccl_gather:
             try:
-                host_frame = tiling.HostFrame(dist, ctx, rank, h, w, n_frames=2)
+                host_frame = tiling.HostFrame(dist, ctx, rank, h, w, n_frames=2, band_rows=BAND_ROWS)
             except Exception as exc:  # noqa: BLE001
                 host_frame = None
                 if rank == 0:
@@ -527,6 +527,9 @@ def main():
         e2e = {"value": rays_total * args.steps / float(t.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": 128 * world,
                "d2h_bytes_per_step": int(n_pix * 4), "ms_per_step": float(t.item()) / args.steps * 1e3, "call": call}
         if host_frame:
+            numa = [host_frame.numa]
+            dist.broadcast_object_list(numa, src=0)
+            e2e["host_frame_numa"] = numa[0]
             host_frame.close()
 
     # clocks: the sampling window covers the K timed steps and the e2e loop; if the timed steps were shorter than
@@ -682,7 +685,7 @@ def extra_block(ctx, torch, rtb200, timer, arrays, bvh, w, h, args):
                    "started (RT_CNT_RAYS_TRACED); parity = bitwise idx/t/u/v against the CPU oracle on the rays named; roofline bytes counted by the oracle"}
     med = lambda ts: float(np.median(ts))
 
-    def passes(tag, arrays, bvh, w, h, light, d_radius=0.0, diffuse_spp=0, check_stride=1, resident=True, frame=True, note=None):
+    def passes(tag, arrays, bvh, w, h, light, d_radius=0.0, diffuse_spp=0, check_stride=1, resident=True, frame=True, note=None, cap=None):
         """primary / shadow / fused primary+shadow (/ diffuse / shaded frame) on the scene the context holds"""
         r = {}
         if note:
@@ -717,7 +720,7 @@ def extra_block(ctx, torch, rtb200, timer, arrays, bvh, w, h, args):
         cnt_full = {"inner": cnt["inner"] * scale, "tris": cnt["tris"] * scale}
         r["primary"] = {"rays": ntrav, "ms": ms, "mrays_s": ntrav / ms / 1e3, "cpu_oracle_mrays_s": sel.size / cpu_s / 1e6,
                         "parity": {"rays_checked": int(sel.size), "bit_identical": ok},
-                        "roofline": roofline_of(cnt_full, 16 * n, ms, "trace_kernel<SRC_PRIMARY,closest>", resident)}
+                        "roofline": roofline_of(cnt_full, 16 * n, ms, "trace_kernel<SRC_PRIMARY,closest>", resident, cap and f"traffic_{cap}_primary")}
         # ---- shadow (any-hit, buffer-fed: rays + closest hits in, records out) ----
         hsel = np.flatnonzero(hits["idx"] >= 0)[::check_stride]
         if hsel.size:
@@ -730,7 +733,7 @@ def extra_block(ctx, torch, rtb200, timer, arrays, bvh, w, h, args):
             cnt_sf = {"inner": cnt_s["inner"] * scale, "tris": cnt_s["tris"] * scale}
             r["shadow_anyhit"] = {"rays": nhit, "ms": ms, "mrays_s": nhit / ms / 1e3, "occluded_fraction": float((want_s["idx"] >= 0).mean()),
                                   "cpu_oracle_mrays_s": hsel.size / cpu_s / 1e6, "parity": {"rays_checked": int(hsel.size), "bit_identical": ok_s},
-                                  "roofline": roofline_of(cnt_sf, 64 * n, ms, "trace_kernel<SRC_SHADOW,any>", resident)}
+                                  "roofline": roofline_of(cnt_sf, 64 * n, ms, "trace_kernel<SRC_SHADOW,any>", resident, cap and f"traffic_{cap}_shadow")}
             # ---- fused: primary + shadow in one launch ----
             d_vis = torch.zeros((h, w), dtype=torch.int32, device="cuda")
             ctx.primary_shadow_device(w, h, None, None, d_vis)
@@ -744,7 +747,7 @@ def extra_block(ctx, torch, rtb200, timer, arrays, bvh, w, h, args):
             cnt_f = {"inner": cnt_full["inner"] + cnt_sf["inner"], "tris": cnt_full["tris"] + cnt_sf["tris"]}
             r["primary_plus_shadow_fused"] = {"rays": rays_f, "ms": ms, "mrays_s": rays_f / ms / 1e3,
                                               "parity": {"pixels_checked": n, "vis_frame_identical_to_two_pass": ok_f},
-                                              "roofline": roofline_of(cnt_f, 4 * n, ms, "primary_shadow_kernel", resident)}
+                                              "roofline": roofline_of(cnt_f, 4 * n, ms, "primary_shadow_kernel", resident, cap and f"traffic_{cap}_fused")}
             ok = ok and ok_s and ok_f
         # ---- incoherent diffuse rays ----
         if diffuse_spp and nhit:
@@ -770,7 +773,7 @@ def extra_block(ctx, torch, rtb200, timer, arrays, bvh, w, h, args):
                                                "parity": {"rays_checked": int(dsel.size), "bit_identical": ok_d},
                                                "inner_visits_per_ray": cnt_d["inner"] / dsel.size, "tri_tests_per_ray": cnt_d["tris"] / dsel.size,
                                                "roofline": roofline_of({"inner": cnt_d["inner"] * scale, "tris": cnt_d["tris"] * scale}, 48 * nd, ms,
-                                                                       "trace_lanes_kernel<SRC_BUFFER,closest>", resident)}
+                                                                       "trace_lanes_kernel<SRC_BUFFER,closest>", resident, cap and f"traffic_{cap}_diffuse")}
             ok = ok and ok_d
             del d_dr, d_dh
         if frame:
@@ -791,7 +794,7 @@ def extra_block(ctx, torch, rtb200, timer, arrays, bvh, w, h, args):
         torch.cuda.empty_cache()
 
     # configs[2]: the bench scene is still uploaded
-    passes("c3_terrain_1M_default_light", arrays, bvh, w, h, (-23.0, 200.0, 3.0), diffuse_spp=4, frame=True)
+    passes("c3_terrain_1M_default_light", arrays, bvh, w, h, (-23.0, 200.0, 3.0), diffuse_spp=4, frame=True, cap="c2")
     passes("c3_terrain_1M_grazing_light", arrays, bvh, w, h, GRAZING_LIGHT, frame=False)
     # frames through the host entry points (pinned frame buffers, wall clock over 50 frames, params set every frame)
     params, _ = rtb200.camera_params(w, h, arrays["aabb_min"], arrays["aabb_max"])
@@ -839,7 +842,8 @@ def extra_block(ctx, torch, rtb200, timer, arrays, bvh, w, h, args):
     b1 = rtb200.FlatBVH.build(m1)
     ctx.upload_scene(a1, b1.nodes, b1.tri_indices)
     passes("c1_sphere_81920_dae_640x480", a1, b1, 640, 480, (-23.0, 200.0, 3.0), diffuse_spp=4,
-           note=f"COLLADA file parsed + baked in {load_s:.2f} s; 75 K traversed rays: launch/latency bound (one tile's critical path is ~45 us)")
+           cap="c1", note=f"COLLADA file parsed + baked in {load_s:.2f} s; 75 K traversed rays = half a wave of 8x4 tiles: launch/latency bound "
+                          "(ncu: SMs active 47 % of the launch, issue active 32 %)")
 
     # configs[3]: incoherent diffuse bounce rays, 4 spp, 10 M-triangle instanced-sphere scene (1.14 GB blob: HBM-resident)
     if not args.skip_c4:
@@ -850,7 +854,10 @@ def extra_block(ctx, torch, rtb200, timer, arrays, bvh, w, h, args):
         build_s = time.time() - t0
         ctx.upload_scene(a4, b4.nodes, b4.tri_indices)
         passes("c4_sphere_field_10M_1080p", a4, b4, 1920, 1080, (-23.0, 200.0, 3.0), d_radius=1320.0, diffuse_spp=4, check_stride=4,
-               resident=False, note=f"scene generated + SBVH built in {build_s:.1f} s on {os.cpu_count()} host threads; parity on every 4th ray")
+               resident=False, cap="c4",
+               note=f"scene generated + SBVH built in {build_s:.1f} s on {os.cpu_count()} host threads; parity on every 4th ray. ncu: DRAM traffic is 0.15-0.25 x "
+                    "the algorithmic bytes (L1 + L2 serve the rest), DRAM throughput 7-12 % of peak: bound by the latency of L2 misses "
+                    "(long-scoreboard stalls, L2 hit 39-61 %) and by SIMT divergence (6-15 of 32 lanes active), not by HBM bandwidth")
         del field, a4, b4
     # leave the context on the bench scene
     ctx.upload_scene(arrays, bvh.nodes, bvh.tri_indices)
