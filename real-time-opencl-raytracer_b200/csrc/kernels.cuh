@@ -89,6 +89,9 @@ __device__ __forceinline__ unsigned int tl_smid() {
 #ifndef RTB_MINB_BATCH
 #define RTB_MINB_BATCH 1
 #endif
+#ifndef RTB_MINB_PRIMARY
+#define RTB_MINB_PRIMARY 8  /* camera-ray batch kernel: 8 blocks x 128 threads = 64 registers, no spills */
+#endif
 #ifndef RTB_MINB_LANES
 #define RTB_MINB_LANES 1
 #endif
@@ -375,7 +378,7 @@ __device__ __forceinline__ void store_ray(float4* rays_out, long long i, const R
 // Grid = (resident blocks per SM) x 148 SMs; every warp pulls 32-ray batches from a global queue
 // head with one atomicAdd by lane 0 + a shuffle, until the queue is empty.
 template <int SRC, bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX = false>
-__global__ void __launch_bounds__(kBlockThreads, (SRC == SRC_PRIMARY && !FAST_BOX) ? 8 : RTB_MINB_BATCH) trace_kernel(const TraceArgs a, int smem_count) {
+__global__ void __launch_bounds__(kBlockThreads, (SRC == SRC_PRIMARY && !FAST_BOX) ? RTB_MINB_PRIMARY : RTB_MINB_BATCH) trace_kernel(const TraceArgs a, int smem_count) {
     extern __shared__ float4 smem_pairs[];
     if (SMEM_TOP) {
         for (int i = threadIdx.x; i < smem_count * 4; i += blockDim.x) smem_pairs[i] = a.scene.pairs[i];
