@@ -285,11 +285,29 @@ __device__ __forceinline__ void sched_init(const TraceArgs& a, unsigned int* s_s
     }
     __syncthreads();
 }
-__device__ __forceinline__ bool next_tile(const TraceArgs& a, const unsigned int* s_sched, int lane, TileWork& tw) {
+// `ahead` (meaningful in lane 0): the queue index fetched one item ahead. A fetch is an atomic on one address that every
+// warp of the GPU hammers -- a ~1 us round trip, 14 of them per warp in a 1080p launch; issued before the current tile is
+// traced and consumed (shuffled) only when the next item is needed, its latency hides behind the tile. The price is that a
+// warp holds one item nobody else can take, which only costs where items are long at the end of the queue: with hints the
+// queue ends on its quickest tiles. Without hints (RTB_NO_QUEUE_PREFETCH builds, or `prefetch` false) the fetch is immediate.
+__device__ __forceinline__ unsigned int queue_fetch(const TraceArgs& a) { return (unsigned int)atomicAdd(a.work_counter, 1ull); }
+#ifdef RTB_NO_QUEUE_PREFETCH
+static constexpr bool kQueuePrefetch = false;
+#else
+static constexpr bool kQueuePrefetch = true;
+#endif
+template <bool PREFETCH>
+__device__ __forceinline__ bool next_tile(const TraceArgs& a, const unsigned int* s_sched, int lane, TileWork& tw, unsigned int& ahead) {
+    const bool prefetch = PREFETCH && a.hint_out != nullptr;
     for (;;) {
         unsigned long long i = 0;
-        if (lane == 0) i = atomicAdd(a.work_counter, 1ull);
-        i = __shfl_sync(0xffffffffu, i, 0);
+        if (prefetch) {
+            i = __shfl_sync(0xffffffffu, ahead, 0);
+            if (lane == 0) ahead = queue_fetch(a);
+        } else {
+            if (lane == 0) i = queue_fetch(a);
+            i = __shfl_sync(0xffffffffu, (unsigned int)i, 0);
+        }
         tw.t0 = (unsigned int)clock();
         const unsigned long long n_split = s_sched[0], n_heavy = s_sched[1];
         if (i < n_split) {
@@ -388,11 +406,13 @@ __global__ void __launch_bounds__(kBlockThreads, (SRC == SRC_PRIMARY && !FAST_BO
     unsigned int traced = 0;
     __shared__ unsigned int s_sched[8];
     if (SRC == SRC_PRIMARY) sched_init(a, s_sched);
+    unsigned int ahead = 0;
+    if (SRC == SRC_PRIMARY && kQueuePrefetch && a.hint_out && lane == 0) ahead = queue_fetch(a);
     for (;;) {
         unsigned long long batch = 0;
         TileWork tw;
         if (SRC == SRC_PRIMARY) {
-            if (!next_tile(a, s_sched, lane, tw)) break;
+            if (!next_tile<kQueuePrefetch>(a, s_sched, lane, tw, ahead)) break;
             batch = (unsigned long long)tw.batch;
         } else {
             if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
@@ -484,9 +504,11 @@ __global__ void __launch_bounds__(kBlockThreads) primary_shadow_kernel(const Tra
     unsigned int traced = 0;
     __shared__ unsigned int s_sched[8];
     sched_init(a, s_sched);
+    unsigned int ahead = 0;
+    if (kQueuePrefetch && a.hint_out && lane == 0) ahead = queue_fetch(a);
     for (;;) {
         TileWork tw;
-        if (!next_tile(a, s_sched, lane, tw)) break;
+        if (!next_tile<kQueuePrefetch>(a, s_sched, lane, tw, ahead)) break;
         const long long batch = tw.batch;
         RTB_TL_BEGIN(a);
         int x, y, tx;
@@ -676,9 +698,10 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_kernel(const TraceArg
     unsigned int traced = 0;
     __shared__ unsigned int s_sched[8];
     sched_init(a, s_sched);
+    unsigned int ahead = 0;  // no fetch-ahead here: the extra live register costs this kernel 120 bytes of spills
     for (;;) {
         TileWork tw;
-        if (!next_tile(a, s_sched, lane, tw)) break;
+        if (!next_tile<false>(a, s_sched, lane, tw, ahead)) break;
         const long long batch = tw.batch;
         RTB_TL_BEGIN(a);
         int x, y, tx;

@@ -543,7 +543,7 @@ static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, size_t sme
 #ifdef RTB_TIMELINE
     a.timeline = ctx->d_timeline;
 #endif
-    CK(ctx, cudaMemsetAsync(counter, 0, zero_bytes, stream));  // queue head (+ the row-assembly arrival counters behind it)
+    if (zero_bytes) CK(ctx, cudaMemsetAsync(counter, 0, zero_bytes, stream));  // queue head (+ the row-assembly arrival counters behind it)
     kernel<<<(unsigned)blocks, kBlockThreads, smem, stream>>>(a, extra...);
     CK(ctx, cudaGetLastError());
     ctx->counters[RT_CNT_KERNEL_LAUNCHES]++;
@@ -561,7 +561,8 @@ enum { HINT_KIND_PRIMARY = 0, HINT_KIND_PRIMARY_SHADOW = 1, HINT_KIND_FRAME = 2 
 // Bind the hint buffers of this launch's frame geometry to `a`: hint_in = what the previous launch of the same geometry
 // (same kernel kind, frame size, band partition and frame slot) recorded, hint_out = where this launch records. Frames in
 // flight on different frame slots have their own slots, so two launches never share a buffer.
-static int attach_hints(rt_context* ctx, int kind, TraceArgs& a, int frame_slot, cudaStream_t stream, rt_context::HintSlot** out_slot) {
+static int attach_hints(rt_context* ctx, int kind, TraceArgs& a, int frame_slot, cudaStream_t stream, rt_context::HintSlot** out_slot,
+                        unsigned long long** counter, size_t* zero_bytes) {
     *out_slot = nullptr;
     a.hint_in = nullptr;
     a.hint_out = nullptr;
@@ -614,7 +615,12 @@ static int attach_hints(rt_context* ctx, int kind, TraceArgs& a, int frame_slot,
     hs->last_use = ++ctx->hint_clock;
     a.hint_in = hs->valid ? hs->buf[hs->cur] : nullptr;
     a.hint_out = hs->buf[hs->cur ^ 1];
-    CK(ctx, cudaMemsetAsync(a.hint_out, 0, kHintHeader * sizeof(unsigned int), stream ? stream : ctx->stream));  // list counts + time sums
+    CK(ctx, cudaMemsetAsync(a.hint_out, 0, kHintHeader * sizeof(unsigned int), stream ? stream : ctx->stream));  // list counts, histogram
+    // a pass without row-assembly counters keeps its work-queue head in the header just zeroed: one memset per launch, not two
+    if (!a.group_log2) {
+        *counter = reinterpret_cast<unsigned long long*>(a.hint_out + 8);
+        *zero_bytes = 0;
+    }
     *out_slot = hs;
     return RT_OK;
 }
@@ -888,7 +894,7 @@ static int primary_impl(rt_context* ctx, int w, int h, int part, int n_parts, in
     if (ctx->opt_scheduler == 1 && !st && d_hits && !d_idx_frame)
         return launch_lanes(ctx, trace_lanes_kernel<SRC_PRIMARY, false>, a, a.num_batches * 32);
     rt_context::HintSlot* hs = nullptr;
-    if ((rc = attach_hints(ctx, HINT_KIND_PRIMARY, a, -1, nullptr, &hs))) return rc;
+    if ((rc = attach_hints(ctx, HINT_KIND_PRIMARY, a, -1, nullptr, &hs, &counter, &zero_bytes))) return rc;
     if (ctx->opt_fast_box && !st)
         rc = launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false, true>, a, 0, nullptr, counter, zero_bytes);
     else
@@ -916,7 +922,7 @@ static int primary_shadow_impl(rt_context* ctx, int w, int h, int part, int n_pa
     size_t zero_bytes = 0;
     if ((rc = frame_sink(ctx, a, d_vis_frame, ctx->rowasm, &counter, &zero_bytes))) return rc;
     rt_context::HintSlot* hs = nullptr;
-    if ((rc = attach_hints(ctx, HINT_KIND_PRIMARY_SHADOW, a, -1, nullptr, &hs))) return rc;
+    if ((rc = attach_hints(ctx, HINT_KIND_PRIMARY_SHADOW, a, -1, nullptr, &hs, &counter, &zero_bytes))) return rc;
     rc = launch_persistent(ctx, primary_shadow_kernel, a, (size_t)0, nullptr, counter, zero_bytes);
     commit_hints(hs, rc);
     return rc;
@@ -1153,7 +1159,7 @@ static int render_frame_impl(rt_context* ctx, int w, int h, int part, int n_part
     if ((rc = frame_sink(ctx, a, d_out, slot >= 0 ? ctx->slots[slot].rowasm : ctx->rowasm, &counter, &zero_bytes))) return rc;
     const int st = smem_top_count(ctx);
     rt_context::HintSlot* hs = nullptr;
-    if ((rc = attach_hints(ctx, HINT_KIND_FRAME, a, slot, stream, &hs))) return rc;
+    if ((rc = attach_hints(ctx, HINT_KIND_FRAME, a, slot, stream, &hs, &counter, &zero_bytes))) return rc;
     rc = st ? launch_persistent(ctx, render_kernel<true>, a, st, stream, counter, zero_bytes)
             : launch_persistent(ctx, render_kernel<false>, a, 0, stream, counter, zero_bytes);
     commit_hints(hs, rc);
