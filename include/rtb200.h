@@ -253,7 +253,7 @@ int rt_set_option(rt_context* ctx, const char* name, int value);
 /* Temporal tile scheduling (option "tile_hints", default 1): a camera-ray launch (rt_primary*, rt_primary_shadow*,
  * rt_render_frame*) records how long each 8x4-pixel tile took; the next launch of the same frame geometry starts the slow
  * tiles first and runs the slowest as four one-row items (DESIGN.md "Tile scheduler"). Results never depend on the hints.
- * Options: "hint_heavy_pct" (12) / "hint_light_pct" (35): the slowest N percent of the tiles start first, the quickest N
+ * Options: "hint_heavy_pct" (12) / "hint_light_pct" (-1 = 35, 65 for shaded frames): the slowest N percent of the tiles start first, the quickest N
  * percent run last; "hint_split_pct" (80), "hint_keep_pct" (30): a tile is split / a row stays split when it took more
  * than that percentage of the previous launch's span (measured: tools/hint_sweep.sh). out: [0] rows on the split list, [1] tiles on the heavy list, [2] tiles timed, [3] launch span
  * (SM cycles) recorded by the most recent such launch. */

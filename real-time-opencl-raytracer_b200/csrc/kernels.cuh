@@ -285,16 +285,16 @@ __device__ __forceinline__ void sched_init(const TraceArgs& a, unsigned int* s_s
     }
     __syncthreads();
 }
-// `ahead` (meaningful in lane 0): the queue index fetched one item ahead. A fetch is an atomic on one address that every
-// warp of the GPU hammers -- a ~1 us round trip, 14 of them per warp in a 1080p launch; issued before the current tile is
-// traced and consumed (shuffled) only when the next item is needed, its latency hides behind the tile. The price is that a
-// warp holds one item nobody else can take, which only costs where items are long at the end of the queue: with hints the
-// queue ends on its quickest tiles. Without hints (RTB_NO_QUEUE_PREFETCH builds, or `prefetch` false) the fetch is immediate.
+// `ahead` (meaningful in lane 0): the queue index fetched one item ahead, so that the ~1 us round trip of the atomic (one
+// address that every warp of the GPU hammers, 14 fetches per warp in a 1080p launch) hides behind the tile. MEASURED SLOWER,
+// twice: round 1 without hints (+14 %: a warp holds an item nobody else can take) and round 2 with hints, where the queue
+// ends on its quickest tiles (1080p primary 0.217 -> 0.240 ms, 4K 1/8-frame fused pass 0.172 -> 0.198 ms,
+// profiles/r2_experiments.md 6). Off unless built with -DRTB_QUEUE_PREFETCH.
 __device__ __forceinline__ unsigned int queue_fetch(const TraceArgs& a) { return (unsigned int)atomicAdd(a.work_counter, 1ull); }
-#ifdef RTB_NO_QUEUE_PREFETCH
-static constexpr bool kQueuePrefetch = false;
-#else
+#ifdef RTB_QUEUE_PREFETCH
 static constexpr bool kQueuePrefetch = true;
+#else
+static constexpr bool kQueuePrefetch = false;
 #endif
 template <bool PREFETCH>
 __device__ __forceinline__ bool next_tile(const TraceArgs& a, const unsigned int* s_sched, int lane, TileWork& tw, unsigned int& ahead) {

@@ -81,7 +81,8 @@ struct rt_context {
     int opt_l2_persist_kb = 0;  // experiment: L2 persisting access window over the first N KB of the node pairs (the BFS-ordered top)
     int opt_tile_hints = 1;     // temporal tile scheduling of the camera-ray kernels (kernels.cuh "tile scheduler")
     int opt_hint_heavy_pct = 12;                        // the slowest N percent of the tiles start first
-    int opt_hint_light_pct = 35;                        // the quickest N percent run last
+    int opt_hint_light_pct = -1;                        // the quickest N percent run last; -1 = 35 (65 for the shaded-frame kernel,
+                                                        // whose normal tiles last long enough to need more cover behind them)
     int opt_hint_split_pct = 80, opt_hint_keep_pct = 30;  // percent of the previous launch's span: split a tile / keep a row split
     // What a launch learnt about its tiles, kept per frame geometry for the next launch of the same geometry. Two buffers
     // per slot: launch k reads the one launch k-1 wrote and writes the other.
@@ -428,7 +429,7 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     else if (!strcmp(name, "l2_persist_kb")) { ctx->opt_l2_persist_kb = value < 0 ? 0 : value; return apply_l2_window(ctx); }
     else if (!strcmp(name, "tile_hints")) { ctx->opt_tile_hints = value ? 1 : 0; forget_hints(ctx); }
     else if (!strcmp(name, "hint_heavy_pct")) { ctx->opt_hint_heavy_pct = value < 1 ? 1 : value; forget_hints(ctx); }
-    else if (!strcmp(name, "hint_light_pct")) { ctx->opt_hint_light_pct = value < 0 ? 0 : (value > 90 ? 90 : value); forget_hints(ctx); }
+    else if (!strcmp(name, "hint_light_pct")) { ctx->opt_hint_light_pct = value < 0 ? -1 : (value > 90 ? 90 : value); forget_hints(ctx); }
     else if (!strcmp(name, "hint_split_pct")) { ctx->opt_hint_split_pct = value < 1 ? 1 : value; forget_hints(ctx); }
     else if (!strcmp(name, "hint_keep_pct")) { ctx->opt_hint_keep_pct = value < 1 ? 1 : value; forget_hints(ctx); }
     else if (!strcmp(name, "top_pairs")) ctx->opt_top_pairs = value < 0 ? 0 : value;  // takes effect at the next upload
@@ -567,7 +568,7 @@ static int attach_hints(rt_context* ctx, int kind, TraceArgs& a, int frame_slot,
     a.hint_in = nullptr;
     a.hint_out = nullptr;
     a.hint_heavy_pct = ctx->opt_hint_heavy_pct;
-    a.hint_light_pct = ctx->opt_hint_light_pct;
+    a.hint_light_pct = ctx->opt_hint_light_pct >= 0 ? ctx->opt_hint_light_pct : (kind == HINT_KIND_FRAME ? 65 : 35);
     a.hint_split_pct = ctx->opt_hint_split_pct;
     a.hint_keep_pct = ctx->opt_hint_keep_pct;
     if (!ctx->opt_tile_hints || a.tile_order != 0 || a.num_batches < 1 || a.num_batches > (1ll << 29)) return RT_OK;
