@@ -154,12 +154,17 @@ __device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, 
         const long long c = batch >> 6;
         if (c < chunks) batch = (long long)(((unsigned long long)c * a.order_mul) % (unsigned long long)chunks) * 64 + (batch & 63);
     }
-    tx = (int)(batch % a.tiles_x);
-    k = batch / a.tiles_x;  // index among this rank's tile rows
-    const long long band = (long long)a.part + (k / a.band_tile_rows) * a.n_parts;
-    const long long tile_row = band * a.band_tile_rows + (k % a.band_tile_rows);
+    // 32-bit index arithmetic: a frame has < 2^31 tiles (band_setup rejects more). The four divisions / remainders below
+    // run once per tile in every lane; as 64-bit operations they were ~10 % of the primary kernel's instructions (ncu).
+    const unsigned int b = (unsigned int)batch, tiles_x = (unsigned int)a.tiles_x, btr = (unsigned int)a.band_tile_rows;
+    const unsigned int kk = b / tiles_x;  // index among this rank's tile rows
+    tx = (int)(b - kk * tiles_x);
+    k = (long long)kk;
+    const unsigned int bk = kk / btr;
+    const unsigned int band = (unsigned int)a.part + bk * (unsigned int)a.n_parts;
+    const unsigned int tile_row = band * btr + (kk - bk * btr);
     x = tx * 8 + (lane & 7);
-    y = (int)(tile_row * 4 + (lane >> 3));
+    y = (int)(tile_row * 4u + (unsigned int)(lane >> 3));
 }
 __device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, int lane, int& x, int& y) {
     int tx;

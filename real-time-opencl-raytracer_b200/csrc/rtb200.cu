@@ -731,6 +731,8 @@ static int band_setup(rt_context* ctx, TraceArgs& a, int w, int h, int part, int
     const long long bands = ((long long)h + band_rows - 1) / band_rows;
     const long long owned = bands > part ? (bands - part + n_parts - 1) / n_parts : 0;
     a.num_batches = owned * a.band_tile_rows * a.tiles_x;
+    if (a.num_batches >= (1ll << 31) || (long long)a.tiles_x * ((h + 3) / 4) >= (1ll << 31))
+        return set_err(ctx, RT_E_INVALID, "frame of %d x %d pixels has too many 8x4 tiles (the kernels index them in 32 bits)", w, h);
     a.tile_order = ctx->opt_tile_order;
     {   // an odd multiplier near 0.618 * count that is coprime to the count being permuted
         const unsigned long long cnt = a.tile_order == 3 ? (unsigned long long)(a.num_batches >> 6) : (unsigned long long)a.num_batches;
