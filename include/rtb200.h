@@ -258,6 +258,8 @@ int rt_set_option(rt_context* ctx, const char* name, int value);
  * than that percentage of the previous launch's span (measured: tools/hint_sweep.sh). out: [0] rows on the split list, [1] tiles on the heavy list, [2] tiles timed, [3] launch span
  * (SM cycles) recorded by the most recent such launch. */
 int rt_tile_hint_stats(rt_context* ctx, uint64_t out[4]);
+/* Option "gate_cull" (default 1): camera-ray launches enumerate only the tiles inside the screen-space bounding rectangle
+ * of the scene box (a pixel outside cannot pass the gate of vR.cl:1196) and write the rest with store-only items. */
 /* GPU self test of the box test's hoisted exact division against the compiler's IEEE division on
  * `samples` random operand pairs; *out_mismatches must come back 0. */
 int rt_selftest(rt_context* ctx, int64_t samples, uint32_t seed, uint64_t* out_mismatches);

@@ -50,6 +50,12 @@ struct TraceArgs {
     unsigned int* group_count;  // one arrival counter per (tile row of this rank, group), zeroed before launch
     int group_log2;             // 0 = off, 2 = 4 tiles (32 px), 4 = 16 tiles (128 px)
     int groups_x;
+    // Scene-box culling of the tile queue (camera-ray kernels, host side: cull_setup in rtb200.cu). Tiles outside the
+    // screen-space bounding rectangle of the scene AABB cannot pass the gate: the queue's main pass enumerates only tile
+    // columns [in_tx0, in_tx1) of this rank's tile rows [in_k0, in_k1), and `n_fill` store-only items (one per 32 tiles of
+    // a tile row) write the miss values of everything outside. n_fill == 0: no culling, the rectangle is the whole frame.
+    int in_tx0, in_tx1, in_k0, in_k1;
+    unsigned int n_fill;
     // Temporal tile scheduling (camera-ray kernels; see "tile scheduler" below): what the previous launch of this frame
     // geometry learnt about its tiles, and where this launch records the same for the next one. Either may be NULL.
     const unsigned int* hint_in;
@@ -146,6 +152,12 @@ __device__ __forceinline__ Ray shadow_ray(f3 light_pos, const Ray& r, float t, f
 
 // Map a primary-ray batch (one warp = one 8x4 pixel tile) to pixel coordinates. tx = tile column, k = index of the tile row
 // among this rank's tile rows (what the row-assembly counters are indexed by).
+// k-th tile row of this rank (interleaved bands of band_tile_rows tile rows) -> tile row of the frame
+__device__ __forceinline__ unsigned int global_tile_row(const TraceArgs& a, unsigned int kk) {
+    const unsigned int btr = (unsigned int)a.band_tile_rows;
+    const unsigned int bk = kk / btr;
+    return ((unsigned int)a.part + bk * (unsigned int)a.n_parts) * btr + (kk - bk * btr);
+}
 __device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, int lane, int& x, int& y, int& tx, long long& k) {
     if (a.tile_order == 1) batch = a.num_batches - 1 - batch;
     else if (a.tile_order == 2) batch = (long long)(((unsigned long long)batch * a.order_mul) % (unsigned long long)a.num_batches);
@@ -156,15 +168,12 @@ __device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, 
     }
     // 32-bit index arithmetic: a frame has < 2^31 tiles (band_setup rejects more). The four divisions / remainders below
     // run once per tile in every lane; as 64-bit operations they were ~10 % of the primary kernel's instructions (ncu).
-    const unsigned int b = (unsigned int)batch, tiles_x = (unsigned int)a.tiles_x, btr = (unsigned int)a.band_tile_rows;
+    const unsigned int b = (unsigned int)batch, tiles_x = (unsigned int)a.tiles_x;
     const unsigned int kk = b / tiles_x;  // index among this rank's tile rows
     tx = (int)(b - kk * tiles_x);
     k = (long long)kk;
-    const unsigned int bk = kk / btr;
-    const unsigned int band = (unsigned int)a.part + bk * (unsigned int)a.n_parts;
-    const unsigned int tile_row = band * btr + (kk - bk * btr);
     x = tx * 8 + (lane & 7);
-    y = (int)(tile_row * 4u + (unsigned int)(lane >> 3));
+    y = (int)(global_tile_row(a, kk) * 4u + (unsigned int)(lane >> 3));
 }
 __device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, int lane, int& x, int& y) {
     int tx;
@@ -242,9 +251,10 @@ __device__ __forceinline__ void finish_tile(const TraceArgs& a, int tx, long lon
 // [H + 4B ..) heavy list: batch;  [H + 5B ..) light list: batch;  [H + 6B ..) one byte per (batch, row): non-zero = that
 // row is covered by a list entry (H = kHintHeader, B = num_batches; the lists can hold every row / tile: no overflow).
 enum { kHintHist = 16, kHintBins = 128, kHintBinShift = 12, kHintHeader = kHintHist + kHintBins };
+static constexpr unsigned int kFillItem = 0x10u;
 struct TileWork {
-    long long batch;
-    unsigned int rows;  // bit r: this warp handles pixel row r of the tile (0xF = the whole tile)
+    long long batch;    // tile index among this rank's tiles (row-major over all tile columns); for a fill item its index
+    unsigned int rows;  // bit r: this warp handles pixel row r of the tile (0xF = the whole tile); kFillItem = a fill item
     unsigned int t0;    // SM clock when the item was fetched
 };
 // s_sched (shared, per block): [0] split entries [1] heavy entries [2] heavy threshold [3] split threshold [4] keep threshold
@@ -301,6 +311,15 @@ static constexpr bool kQueuePrefetch = true;
 #else
 static constexpr bool kQueuePrefetch = false;
 #endif
+// Is tile `batch` inside the rectangle the queue enumerates? A list entry recorded under another rectangle (the camera
+// moved, or the frame of the previous launch was assembled in wider groups) may lie outside now: it is dropped -- the fill
+// items own everything outside, and every (tile, row) must have exactly ONE owner per launch (a second arrival would
+// overshoot the row-assembly counter of its group, and a re-listed tile would be traced twice next time).
+__device__ __forceinline__ bool tile_in_rect(const TraceArgs& a, long long batch) {
+    const unsigned int b = (unsigned int)batch, kk = b / (unsigned int)a.tiles_x;
+    const int tx = (int)(b - kk * (unsigned int)a.tiles_x);
+    return (int)kk >= a.in_k0 && (int)kk < a.in_k1 && tx >= a.in_tx0 && tx < a.in_tx1;
+}
 template <bool PREFETCH>
 __device__ __forceinline__ bool next_tile(const TraceArgs& a, const unsigned int* s_sched, int lane, TileWork& tw, unsigned int& ahead) {
     const bool prefetch = PREFETCH && a.hint_out != nullptr;
@@ -320,30 +339,41 @@ __device__ __forceinline__ bool next_tile(const TraceArgs& a, const unsigned int
             const unsigned int e = __ldg(a.hint_in + kHintHeader + (n_split - 1 - i));
             tw.batch = (long long)(e >> 2);
             tw.rows = 1u << (e & 3u);
-            if (tw.batch >= a.num_batches) continue;  // cannot happen with a buffer this launch geometry wrote; never trust it
+            if (tw.batch >= a.num_batches || !tile_in_rect(a, tw.batch)) continue;  // (an index past the end cannot happen; never trust it)
             return true;
         }
         i -= n_split;
         if (i < n_heavy) {
             tw.batch = (long long)__ldg(a.hint_in + kHintHeader + 4 * a.num_batches + (n_heavy - 1 - i));
             tw.rows = 0xFu;
-            if (tw.batch >= a.num_batches) continue;
+            if (tw.batch >= a.num_batches || !tile_in_rect(a, tw.batch)) continue;
             return true;
         }
         i -= n_heavy;
-        if (i >= (unsigned long long)a.num_batches) {  // after the main pass: the light tiles, the slowest of them first
-            i -= (unsigned long long)a.num_batches;
+        const unsigned int wx = (unsigned int)(a.in_tx1 - a.in_tx0);
+        const unsigned long long n_main = (unsigned long long)wx * (unsigned int)(a.in_k1 - a.in_k0);
+        if (i >= n_main) {  // after the main pass: the light tiles, the slowest of them first
+            i -= n_main;
             const unsigned long long n_light = s_sched[6];
-            if (i >= n_light) return false;
+            if (i >= n_light) {  // and last the store-only items for what lies outside the scene box's rectangle
+                i -= n_light;
+                if (i >= a.n_fill) return false;
+                tw.batch = (long long)i;
+                tw.rows = kFillItem;
+                return true;
+            }
             tw.batch = (long long)__ldg(a.hint_in + kHintHeader + 5 * a.num_batches + (n_light - 1 - i));
             tw.rows = 0xFu;
-            if (tw.batch >= a.num_batches) continue;
+            if (tw.batch >= a.num_batches || !tile_in_rect(a, tw.batch)) continue;
             return true;
         }
-        tw.batch = (long long)i;
+        {   // main pass: the tiles inside the rectangle, row-major
+            const unsigned int j = (unsigned int)i, jr = j / wx;
+            tw.batch = (long long)((unsigned int)(a.in_k0 + jr) * (unsigned int)a.tiles_x + (unsigned int)a.in_tx0 + (j - jr * wx));
+        }
         tw.rows = 0xFu;
         if (a.hint_in) {  // rows that a list entry covers were (or will be) traced by that entry's warp
-            const unsigned int f = __ldg(a.hint_in + kHintHeader + 6 * a.num_batches + i);
+            const unsigned int f = __ldg(a.hint_in + kHintHeader + 6 * a.num_batches + tw.batch);
             const unsigned int covered = ((f & 0xffu) ? 1u : 0u) | ((f & 0xff00u) ? 2u : 0u) | ((f & 0xff0000u) ? 4u : 0u) | ((f & 0xff000000u) ? 8u : 0u);
             tw.rows = 0xFu & ~covered;
             if (!tw.rows) continue;
@@ -391,6 +421,33 @@ __device__ __forceinline__ void record_tile(const TraceArgs& a, const unsigned i
 __device__ __forceinline__ void record_span(const TraceArgs& a, const unsigned int* s_sched, int lane) {
     if (a.hint_out && lane == 0) atomicMax(a.hint_out + 3, (unsigned int)clock() - s_sched[5]);
 }
+// A fill item: 32 tiles (256 x 4 pixels) of one tile row; every pixel of it that lies outside the scene box's rectangle
+// gets the values a gated-out pixel gets -- the miss record(s) and `frame_miss` in the 4-byte frame (written to the
+// destination itself: groups of tiles outside the rectangle are never row-assembled) -- in 512-byte row segments, and
+// the tiles' hint flags are cleared so that a later launch which finds them inside does not read a stale class.
+__device__ __forceinline__ void fill_outside(const TraceArgs& a, int lane, unsigned int item, unsigned int frame_miss) {
+    const unsigned int segs = ((unsigned int)a.tiles_x + 31u) >> 5;
+    const unsigned int kk = item / segs, seg = item - kk * segs;
+    const bool row_inside = (int)kk >= a.in_k0 && (int)kk < a.in_k1;
+    const int y0 = (int)(global_tile_row(a, kk) * 4u);
+    const float4 miss = make_float4(__int_as_float(-1), RTB_T_INIT, 0.0f, 0.0f);
+    for (int c = 0; c < 8; c++) {
+        const int x = (int)(seg * 256u) + c * 32 + lane;
+        const int tx = x >> 3;
+        if (x >= a.w || (row_inside && tx >= a.in_tx0 && tx < a.in_tx1)) continue;
+        for (int r = 0; r < 4 && y0 + r < a.h; r++) {
+            const size_t px = (size_t)(y0 + r) * a.w + x;
+            if (a.hits_out) a.hits_out[px] = miss;
+            if (a.shadow_hits_out) a.shadow_hits_out[px] = miss;
+            if (a.frame_out) a.frame_out[px] = frame_miss;
+        }
+    }
+    if (a.hint_out) {
+        const int tx = (int)(seg * 32u) + lane;
+        if (tx < a.tiles_x && !(row_inside && tx >= a.in_tx0 && tx < a.in_tx1))
+            a.hint_out[kHintHeader + 6 * a.num_batches + (size_t)kk * a.tiles_x + tx] = 0u;
+    }
+}
 
 __device__ __forceinline__ void store_ray(float4* rays_out, long long i, const Ray& r) {
     rays_out[2 * i] = make_float4(r.ori.x, r.ori.y, r.ori.z, RTB_T_INIT);
@@ -418,6 +475,10 @@ __global__ void __launch_bounds__(kBlockThreads, (SRC == SRC_PRIMARY && !FAST_BO
         TileWork tw;
         if (SRC == SRC_PRIMARY) {
             if (!next_tile<kQueuePrefetch>(a, s_sched, lane, tw, ahead)) break;
+            if (tw.rows == kFillItem) {
+                fill_outside(a, lane, (unsigned int)tw.batch, 0xffffffffu);
+                continue;
+            }
             batch = (unsigned long long)tw.batch;
         } else {
             if (lane == 0) batch = atomicAdd(a.work_counter, 1ull);
@@ -514,6 +575,10 @@ __global__ void __launch_bounds__(kBlockThreads) primary_shadow_kernel(const Tra
     for (;;) {
         TileWork tw;
         if (!next_tile<kQueuePrefetch>(a, s_sched, lane, tw, ahead)) break;
+        if (tw.rows == kFillItem) {
+            fill_outside(a, lane, (unsigned int)tw.batch, 0xffffffffu);
+            continue;
+        }
         const long long batch = tw.batch;
         RTB_TL_BEGIN(a);
         int x, y, tx;
@@ -707,6 +772,10 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_kernel(const TraceArg
     for (;;) {
         TileWork tw;
         if (!next_tile<false>(a, s_sched, lane, tw, ahead)) break;
+        if (tw.rows == kFillItem) {
+            fill_outside(a, lane, (unsigned int)tw.batch, 0u);  // a pixel that fails the gate is black (vR.cl:1542)
+            continue;
+        }
         const long long batch = tw.batch;
         RTB_TL_BEGIN(a);
         int x, y, tx;

@@ -7,6 +7,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -79,6 +80,7 @@ struct rt_context {
     int opt_store_group = -1;   // row assembly of 4-byte/pixel frames: -1 = auto (on when the frame is host or peer memory),
                                 // 0 = off, 2 = groups of 4 tiles (128-byte rows), 4 = groups of 16 tiles (512-byte rows)
     int opt_l2_persist_kb = 0;  // experiment: L2 persisting access window over the first N KB of the node pairs (the BFS-ordered top)
+    int opt_gate_cull = 1;      // camera-ray kernels: tiles outside the scene box's screen rectangle leave the queue (cull_setup)
     int opt_tile_hints = 1;     // temporal tile scheduling of the camera-ray kernels (kernels.cuh "tile scheduler")
     int opt_hint_heavy_pct = 12;                        // the slowest N percent of the tiles start first
     int opt_hint_light_pct = -1;                        // the quickest N percent run last; -1 = 35 (65 for the shaded-frame kernel,
@@ -427,6 +429,7 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     } else if (!strcmp(name, "overlap_frames")) ctx->opt_overlap_frames = value ? 1 : 0;
     else if (!strcmp(name, "store_group")) ctx->opt_store_group = (value == 0 || value == 2 || value == 4) ? value : -1;
     else if (!strcmp(name, "l2_persist_kb")) { ctx->opt_l2_persist_kb = value < 0 ? 0 : value; return apply_l2_window(ctx); }
+    else if (!strcmp(name, "gate_cull")) ctx->opt_gate_cull = value ? 1 : 0;
     else if (!strcmp(name, "tile_hints")) { ctx->opt_tile_hints = value ? 1 : 0; forget_hints(ctx); }
     else if (!strcmp(name, "hint_heavy_pct")) { ctx->opt_hint_heavy_pct = value < 1 ? 1 : value; forget_hints(ctx); }
     else if (!strcmp(name, "hint_light_pct")) { ctx->opt_hint_light_pct = value < 0 ? -1 : (value > 90 ? 90 : value); forget_hints(ctx); }
@@ -557,6 +560,100 @@ static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, int smem_c
     return launch_persistent(ctx, kernel, a, (size_t)smem_count * 64, stream, counter, zero_bytes, smem_count);
 }
 
+// ---- scene-box culling of the tile queue ---------------------------------------------------------------------------------
+// A pixel traverses only if its ray passes the scene-AABB gate (vR.cl:1196); on the bench frame 64 % of the 8x4 tiles hold no
+// such pixel, and fetching + testing them one by one was ~5 % of a launch's warp time (40 us of fixed cost for 1/8 of a 4K
+// frame). The rays start ON the image plane and leave the eye, so every point they can reach is campos + lambda * (image_pos
+// - campos) with lambda >= 1: the pixels whose rays can touch the box lie inside the bounding rectangle of the box corners
+// projected through the eye onto the image plane -- provided every corner is in front of the plane. That rectangle, grown by
+// two pixels (the device decides each pixel with fp32 arithmetic; its error is ~1e-6 of the frame) and to tile / row-assembly
+// group boundaries, is what the queue enumerates; everything outside is written by store-only fill items. A camera inside or
+// beside the box, a degenerate basis or non-finite numbers leave the rectangle at the whole frame.
+static bool stores_to_host_memory(const TraceArgs& a) {
+    auto in_host_memory = [](const void* p) {
+        if (!p) return false;
+        cudaPointerAttributes attr;
+        memset(&attr, 0, sizeof attr);
+        if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return attr.type == cudaMemoryTypeHost;
+    };
+    return in_host_memory(a.frame_out) || in_host_memory(a.hits_out) || in_host_memory(a.shadow_hits_out);
+}
+
+static void cull_setup(const rt_context* ctx, TraceArgs& a) {
+    const int tile_rows_total = (a.h + 3) / 4;
+    const long long K = a.tiles_x ? a.num_batches / a.tiles_x : 0;  // this rank's tile rows
+    a.in_tx0 = 0;
+    a.in_tx1 = a.tiles_x;
+    a.in_k0 = 0;
+    a.in_k1 = (int)K;
+    a.n_fill = 0;
+    // (a pass that stores straight into host memory is paced by PCIe and wants its stores -- two thirds of them miss records
+    // -- spread over the launch, not bunched in fill items at the end: it keeps the plain enumeration, like it keeps the plain queue)
+    if (!ctx->opt_gate_cull || a.rays_out || a.tile_order != 0 || K < 1 || stores_to_host_memory(a)) return;
+    const ParamsBlock& P = a.params;
+    const double A[3] = {P.a.x, P.a.y, P.a.z}, B[3] = {P.b.x, P.b.y, P.b.z}, Cc[3] = {P.c.x, P.c.y, P.c.z};
+    const double E[3] = {P.campos.x, P.campos.y, P.campos.z};
+    const double lo[3] = {P.aabb_min.x, P.aabb_min.y, P.aabb_min.z}, hi[3] = {P.aabb_max.x, P.aabb_max.y, P.aabb_max.z};
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    for (int corner = 0; corner < 8; corner++) {
+        double D[3], R[3];  // D = corner - eye, R = eye - c;  solve  A xf + B yf - D s = R
+        for (int i = 0; i < 3; i++) {
+            D[i] = ((corner >> i) & 1 ? hi[i] : lo[i]) - E[i];
+            R[i] = E[i] - Cc[i];
+        }
+        auto det3 = [](const double* u, const double* v, const double* w) {
+            return u[0] * (v[1] * w[2] - v[2] * w[1]) - v[0] * (u[1] * w[2] - u[2] * w[1]) + w[0] * (u[1] * v[2] - u[2] * v[1]);
+        };
+        const double nD[3] = {-D[0], -D[1], -D[2]};
+        const double det = det3(A, B, nD);
+        if (!(std::fabs(det) > 1e-300)) return;
+        const double xf = det3(R, B, nD) / det, yf = det3(A, R, nD) / det, sc = det3(A, B, R) / det;
+        if (!(sc > 1e-9 && sc <= 1.0) || !std::isfinite(xf) || !std::isfinite(yf)) return;  // corner not beyond the image plane
+        const double px = xf * a.w + 0.5, py = yf * a.h + 0.5;  // xf = (x - 0.5) / w
+        xmin = px < xmin ? px : xmin; xmax = px > xmax ? px : xmax;
+        ymin = py < ymin ? py : ymin; ymax = py > ymax ? py : ymax;
+    }
+    const double margin = 2.0;
+    long long x0 = (long long)std::floor(xmin - margin), x1 = (long long)std::ceil(xmax + margin);   // pixel columns [x0, x1]
+    long long y0 = (long long)std::floor(ymin - margin), y1 = (long long)std::ceil(ymax + margin);
+    if (x0 < 0) x0 = 0;
+    if (y0 < 0) y0 = 0;
+    if (x1 > a.w - 1) x1 = a.w - 1;
+    if (y1 > a.h - 1) y1 = a.h - 1;
+    int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;  // empty when the box is off screen
+    if (x0 <= x1 && y0 <= y1) {
+        tx0 = (int)(x0 / 8); tx1 = (int)(x1 / 8) + 1;
+        ty0 = (int)(y0 / 4); ty1 = (int)(y1 / 4) + 1;
+        if (a.group_log2) {  // whole row-assembly groups: a group is either traced (and assembled) or filled
+            const int g = 1 << a.group_log2;
+            tx0 = tx0 / g * g;
+            tx1 = (tx1 + g - 1) / g * g;
+            if (tx1 > a.tiles_x) tx1 = a.tiles_x;
+        }
+        if (ty1 > tile_rows_total) ty1 = tile_rows_total;
+    }
+    // this rank's tile rows are ascending in the frame: the ones inside [ty0, ty1) form one run [k0, k1)
+    int k0 = (int)K, k1 = (int)K;
+    for (long long k = 0; k < K; k++) {
+        const long long bk = k / a.band_tile_rows;
+        const long long row = ((long long)a.part + bk * a.n_parts) * a.band_tile_rows + (k - bk * a.band_tile_rows);
+        if (row >= ty0 && row < ty1) {
+            if (k0 == (int)K) k0 = (int)k;
+            k1 = (int)k + 1;
+        }
+    }
+    if (k0 == (int)K) k0 = k1 = 0;
+    if (tx0 >= tx1) { tx0 = tx1 = 0; k0 = k1 = 0; }
+    const long long inside = (long long)(k1 - k0) * (tx1 - tx0);
+    if (inside * 10 > a.num_batches * 9) return;  // nothing worth culling: keep the plain enumeration
+    a.in_tx0 = tx0; a.in_tx1 = tx1; a.in_k0 = k0; a.in_k1 = k1;
+    a.n_fill = (unsigned int)(K * ((a.tiles_x + 31) / 32));
+}
+
 // ---- temporal tile scheduling: hint slots (device side: kernels.cuh "tile scheduler") -----------------------------------
 enum { HINT_KIND_PRIMARY = 0, HINT_KIND_PRIMARY_SHADOW = 1, HINT_KIND_FRAME = 2 };
 // Bind the hint buffers of this launch's frame geometry to `a`: hint_in = what the previous launch of the same geometry
@@ -575,17 +672,7 @@ static int attach_hints(rt_context* ctx, int kind, TraceArgs& a, int frame_slot,
     // A pass that stores straight into host memory is paced by the PCIe link, which wants the stores spread evenly over
     // the launch; starting the slow tiles first and ending on the quick ones bunches the stores at the end (measured:
     // rt_primary into pinned memory 0.71 -> 0.78 ms). Such passes keep the plain row-major queue.
-    auto in_host_memory = [](const void* p) {
-        if (!p) return false;
-        cudaPointerAttributes attr;
-        memset(&attr, 0, sizeof attr);
-        if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        return attr.type == cudaMemoryTypeHost;
-    };
-    if (in_host_memory(a.frame_out) || in_host_memory(a.hits_out) || in_host_memory(a.shadow_hits_out)) return RT_OK;
+    if (stores_to_host_memory(a)) return RT_OK;
     rt_context::HintSlot* hs = nullptr;
     rt_context::HintSlot* lru = &ctx->hint_slots[0];
     for (auto& c : ctx->hint_slots) {
@@ -896,6 +983,7 @@ static int primary_impl(rt_context* ctx, int w, int h, int part, int n_parts, in
     const int st = smem_top_count(ctx);
     if (ctx->opt_scheduler == 1 && !st && d_hits && !d_idx_frame)
         return launch_lanes(ctx, trace_lanes_kernel<SRC_PRIMARY, false>, a, a.num_batches * 32);
+    cull_setup(ctx, a);
     rt_context::HintSlot* hs = nullptr;
     if ((rc = attach_hints(ctx, HINT_KIND_PRIMARY, a, -1, nullptr, &hs, &counter, &zero_bytes))) return rc;
     if (ctx->opt_fast_box && !st)
@@ -924,6 +1012,7 @@ static int primary_shadow_impl(rt_context* ctx, int w, int h, int part, int n_pa
     unsigned long long* counter = nullptr;
     size_t zero_bytes = 0;
     if ((rc = frame_sink(ctx, a, d_vis_frame, ctx->rowasm, &counter, &zero_bytes))) return rc;
+    cull_setup(ctx, a);
     rt_context::HintSlot* hs = nullptr;
     if ((rc = attach_hints(ctx, HINT_KIND_PRIMARY_SHADOW, a, -1, nullptr, &hs, &counter, &zero_bytes))) return rc;
     rc = launch_persistent(ctx, primary_shadow_kernel, a, (size_t)0, nullptr, counter, zero_bytes);
@@ -1161,6 +1250,7 @@ static int render_frame_impl(rt_context* ctx, int w, int h, int part, int n_part
     size_t zero_bytes = sizeof(unsigned long long);
     if ((rc = frame_sink(ctx, a, d_out, slot >= 0 ? ctx->slots[slot].rowasm : ctx->rowasm, &counter, &zero_bytes))) return rc;
     const int st = smem_top_count(ctx);
+    cull_setup(ctx, a);
     rt_context::HintSlot* hs = nullptr;
     if ((rc = attach_hints(ctx, HINT_KIND_FRAME, a, slot, stream, &hs, &counter, &zero_bytes))) return rc;
     rc = st ? launch_persistent(ctx, render_kernel<true>, a, st, stream, counter, zero_bytes)

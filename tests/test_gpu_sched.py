@@ -143,3 +143,80 @@ def test_frames_in_flight_keep_their_own_hints(ctx):
         ctx.set_option("tile_hints", 1)
         for k, v in (("hint_heavy_pct", 12), ("hint_split_pct", 80), ("hint_keep_pct", 30)):
             ctx.set_option(k, v)
+
+
+@pytest.mark.parametrize("pose", [dict(), dict(d_radius=-120.0), dict(d_radius=-195.0), dict(d_radius=400.0, d_alpha=0.7, d_beta=0.3),
+                                  dict(d_alpha=2.0, d_beta=-0.6), dict(d_radius=-150.0, d_beta=-0.7)],
+                         ids=["default", "close", "inside_the_box", "far_rotated", "rotated", "low_and_close"])
+@pytest.mark.parametrize("parts", [(0, 1, 4), (1, 3, 8)])
+def test_scene_box_culling_never_changes_a_result(ctx, pose, parts):
+    """the tile queue enumerates only the screen rectangle of the scene box and fills the rest (cull_setup): every output of
+    every camera-ray entry point, and the number of rays traced, equal the unculled launch -- camera far, close, inside the
+    box (no rectangle: whole frame), with and without row assembly, with the tile hints on"""
+    import torch
+
+    w, h = 424, 244
+    part, n_parts, band_rows = parts
+    A = _scene(ctx)
+    params, _ = rtb200.camera_params(w, h, A["aabb_min"], A["aabb_max"], light_pos=GRAZING, **pose)
+    ctx.set_params(params)
+    kw = dict(part=part, n_parts=n_parts, band_rows=band_rows)
+
+    def run_all(store_group):
+        ctx.set_option("store_group", store_group)
+        hits = torch.full((w * h, 4), -7.0, device="cuda")
+        sh = torch.full((w * h, 4), -7.0, device="cuda")
+        idx = torch.full((h, w), -5, dtype=torch.int32, device="cuda")
+        vis = torch.full((h, w), -5, dtype=torch.int32, device="cuda")
+        img = torch.full((h, w), -5, dtype=torch.int32, device="cuda")
+        ctx.reset_counters()
+        ctx.primary_device(w, h, hits, **kw)
+        ctx.primary_gather_device(w, h, None, idx, **kw)
+        ctx.primary_shadow_device(w, h, None, sh, vis, **kw)
+        ctx.render_frame_device(w, h, img, **kw)
+        ctx.synchronize()
+        return [t.cpu().numpy().copy() for t in (hits, sh, idx, vis, img)], ctx.counters()["rays_traced"]
+
+    try:
+        ctx.set_option("gate_cull", 0)
+        ctx.set_option("tile_hints", 0)
+        want, want_rays = run_all(0)
+        ctx.set_option("gate_cull", 1)
+        _force_hints(ctx, True)
+        for it in range(6):
+            got, rays = run_all((0, 2, 4)[it % 3])
+            for name, g, wnt in zip(("hits", "shadow hits", "index frame", "visibility frame", "shaded frame"), got, want):
+                assert np.array_equal(g.view(np.uint32), wnt.view(np.uint32)), f"launch {it}: {name} changed with the culled queue"
+            assert rays == want_rays, (rays, want_rays)
+    finally:
+        ctx.set_option("store_group", -1)
+        ctx.set_option("gate_cull", 1)
+        ctx.set_option("tile_hints", 1)
+        for k, v in (("hint_heavy_pct", 12), ("hint_split_pct", 80), ("hint_keep_pct", 30)):
+            ctx.set_option(k, v)
+
+
+def test_culled_queue_follows_a_moving_camera(ctx):
+    """hints recorded under one rectangle, a different rectangle in the next launch (the camera zooms and orbits): tiles
+    change sides between launches and still every frame equals the unculled, hint-free one"""
+    w, h = 384, 216
+    A = _scene(ctx)
+    ref = rtb200.Context(0)
+    ref.set_option("tile_hints", 0)
+    ref.set_option("gate_cull", 0)
+    m = rtb200.Mesh().terrain(96, 100.0).icosphere(3, 22.0, (15.0, 28.0, -20.0)).finish(diffuse=(0.6, 0.7, 0.8))
+    b = rtb200.FlatBVH.build(m)
+    ref.upload_scene(m.arrays(), b.nodes, b.tri_indices)
+    try:
+        _force_hints(ctx, True)
+        for step in range(8):
+            params, _ = rtb200.camera_params(w, h, A["aabb_min"], A["aabb_max"], d_radius=-40.0 * step + 100.0, d_alpha=0.25 * step, d_beta=0.04 * step)
+            for c in (ctx, ref):
+                c.set_params(params)
+            assert np.array_equal(ctx.render_frame(w, h), ref.render_frame(w, h)), f"step {step}"
+            assert np.array_equal(ctx.primary_shadow(w, h), ref.primary_shadow(w, h)), f"step {step}"
+    finally:
+        ref.close()
+        ctx.set_option("tile_hints", 1)
+        for k, v in (("hint_heavy_pct", 12), ("hint_split_pct", 80), ("hint_keep_pct", 30)):
+            ctx.set_option(k, v)
