@@ -259,7 +259,10 @@ int rt_set_option(rt_context* ctx, const char* name, int value);
  * (SM cycles) recorded by the most recent such launch. */
 int rt_tile_hint_stats(rt_context* ctx, uint64_t out[4]);
 /* Option "gate_cull" (default 1): camera-ray launches enumerate only the tiles inside the screen-space bounding rectangle
- * of the scene box (a pixel outside cannot pass the gate of vR.cl:1196) and write the rest with store-only items. */
+ * of the scene box (a pixel outside cannot pass the gate of vR.cl:1196) and write the rest with store-only items.
+ * rt_cull_rect_host (no device needed) returns that rectangle in pixels, inclusive: [x0, x1] x [y0, y1] (x0 > x1 or y0 > y1:
+ * the box is off screen; the whole frame when no bound is known, e.g. the eye is inside the box). */
+int rt_cull_rect_host(const float params[32], int w, int h, int64_t out_x0_x1_y0_y1[4]);
 /* GPU self test of the box test's hoisted exact division against the compiler's IEEE division on
  * `samples` random operand pairs; *out_mismatches must come back 0. */
 int rt_selftest(rt_context* ctx, int64_t samples, uint32_t seed, uint64_t* out_mismatches);

@@ -583,6 +583,55 @@ static bool stores_to_host_memory(const TraceArgs& a) {
     return in_host_memory(a.frame_out) || in_host_memory(a.hits_out) || in_host_memory(a.shadow_hits_out);
 }
 
+// Inclusive pixel bounds [x0, x1] x [y0, y1] (clamped to the frame; x0 > x1 or y0 > y1: nothing on screen) of every pixel
+// whose ray can pass the scene gate, or false when no such bound is known (a box corner is not beyond the image plane).
+static bool cull_pixel_rect(const ParamsBlock& P, int w, int h, long long out[4]) {
+    const double A[3] = {P.a.x, P.a.y, P.a.z}, B[3] = {P.b.x, P.b.y, P.b.z}, Cc[3] = {P.c.x, P.c.y, P.c.z};
+    const double E[3] = {P.campos.x, P.campos.y, P.campos.z};
+    const double lo[3] = {P.aabb_min.x, P.aabb_min.y, P.aabb_min.z}, hi[3] = {P.aabb_max.x, P.aabb_max.y, P.aabb_max.z};
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    for (int corner = 0; corner < 8; corner++) {
+        double D[3], R[3];  // D = corner - eye, R = eye - c;  solve  A xf + B yf - D s = R
+        for (int i = 0; i < 3; i++) {
+            D[i] = ((corner >> i) & 1 ? hi[i] : lo[i]) - E[i];
+            R[i] = E[i] - Cc[i];
+        }
+        auto det3 = [](const double* u, const double* v, const double* w3) {
+            return u[0] * (v[1] * w3[2] - v[2] * w3[1]) - v[0] * (u[1] * w3[2] - u[2] * w3[1]) + w3[0] * (u[1] * v[2] - u[2] * v[1]);
+        };
+        const double nD[3] = {-D[0], -D[1], -D[2]};
+        const double det = det3(A, B, nD);
+        if (!(std::fabs(det) > 1e-300)) return false;
+        const double xf = det3(R, B, nD) / det, yf = det3(A, R, nD) / det, sc = det3(A, B, R) / det;
+        if (!(sc > 1e-9 && sc <= 1.0) || !std::isfinite(xf) || !std::isfinite(yf)) return false;  // corner not beyond the image plane
+        const double px = xf * w + 0.5, py = yf * h + 0.5;  // xf = (x - 0.5) / w
+        xmin = px < xmin ? px : xmin; xmax = px > xmax ? px : xmax;
+        ymin = py < ymin ? py : ymin; ymax = py > ymax ? py : ymax;
+    }
+    if (!(xmax - xmin < 1e15) || !(ymax - ymin < 1e15)) return false;
+    const double margin = 2.0;
+    long long x0 = (long long)std::floor(xmin - margin), x1 = (long long)std::ceil(xmax + margin);
+    long long y0 = (long long)std::floor(ymin - margin), y1 = (long long)std::ceil(ymax + margin);
+    if (x0 < 0) x0 = 0;
+    if (y0 < 0) y0 = 0;
+    if (x1 > w - 1) x1 = w - 1;
+    if (y1 > h - 1) y1 = h - 1;
+    out[0] = x0; out[1] = x1; out[2] = y0; out[3] = y1;
+    return true;
+}
+// Host-only probe of the rectangle (tests/test_cull_rect.py checks it against the oracle's gate pixel by pixel).
+extern "C" int rt_cull_rect_host(const float params[32], int w, int h, int64_t out_x0_x1_y0_y1[4]) {
+    if (!params || !out_x0_x1_y0_y1 || w <= 0 || h <= 0) return RT_E_INVALID;
+    ParamsBlock P;
+    memcpy(&P, params, sizeof P);
+    long long r[4];
+    if (!cull_pixel_rect(P, w, h, r)) {  // unknown: the whole frame
+        r[0] = 0; r[1] = w - 1; r[2] = 0; r[3] = h - 1;
+    }
+    for (int i = 0; i < 4; i++) out_x0_x1_y0_y1[i] = r[i];
+    return RT_OK;
+}
+
 static void cull_setup(const rt_context* ctx, TraceArgs& a) {
     const int tile_rows_total = (a.h + 3) / 4;
     const long long K = a.tiles_x ? a.num_batches / a.tiles_x : 0;  // this rank's tile rows
@@ -594,36 +643,9 @@ static void cull_setup(const rt_context* ctx, TraceArgs& a) {
     // (a pass that stores straight into host memory is paced by PCIe and wants its stores -- two thirds of them miss records
     // -- spread over the launch, not bunched in fill items at the end: it keeps the plain enumeration, like it keeps the plain queue)
     if (!ctx->opt_gate_cull || a.rays_out || a.tile_order != 0 || K < 1 || stores_to_host_memory(a)) return;
-    const ParamsBlock& P = a.params;
-    const double A[3] = {P.a.x, P.a.y, P.a.z}, B[3] = {P.b.x, P.b.y, P.b.z}, Cc[3] = {P.c.x, P.c.y, P.c.z};
-    const double E[3] = {P.campos.x, P.campos.y, P.campos.z};
-    const double lo[3] = {P.aabb_min.x, P.aabb_min.y, P.aabb_min.z}, hi[3] = {P.aabb_max.x, P.aabb_max.y, P.aabb_max.z};
-    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
-    for (int corner = 0; corner < 8; corner++) {
-        double D[3], R[3];  // D = corner - eye, R = eye - c;  solve  A xf + B yf - D s = R
-        for (int i = 0; i < 3; i++) {
-            D[i] = ((corner >> i) & 1 ? hi[i] : lo[i]) - E[i];
-            R[i] = E[i] - Cc[i];
-        }
-        auto det3 = [](const double* u, const double* v, const double* w) {
-            return u[0] * (v[1] * w[2] - v[2] * w[1]) - v[0] * (u[1] * w[2] - u[2] * w[1]) + w[0] * (u[1] * v[2] - u[2] * v[1]);
-        };
-        const double nD[3] = {-D[0], -D[1], -D[2]};
-        const double det = det3(A, B, nD);
-        if (!(std::fabs(det) > 1e-300)) return;
-        const double xf = det3(R, B, nD) / det, yf = det3(A, R, nD) / det, sc = det3(A, B, R) / det;
-        if (!(sc > 1e-9 && sc <= 1.0) || !std::isfinite(xf) || !std::isfinite(yf)) return;  // corner not beyond the image plane
-        const double px = xf * a.w + 0.5, py = yf * a.h + 0.5;  // xf = (x - 0.5) / w
-        xmin = px < xmin ? px : xmin; xmax = px > xmax ? px : xmax;
-        ymin = py < ymin ? py : ymin; ymax = py > ymax ? py : ymax;
-    }
-    const double margin = 2.0;
-    long long x0 = (long long)std::floor(xmin - margin), x1 = (long long)std::ceil(xmax + margin);   // pixel columns [x0, x1]
-    long long y0 = (long long)std::floor(ymin - margin), y1 = (long long)std::ceil(ymax + margin);
-    if (x0 < 0) x0 = 0;
-    if (y0 < 0) y0 = 0;
-    if (x1 > a.w - 1) x1 = a.w - 1;
-    if (y1 > a.h - 1) y1 = a.h - 1;
+    long long rect[4];
+    if (!cull_pixel_rect(a.params, a.w, a.h, rect)) return;
+    const long long x0 = rect[0], x1 = rect[1], y0 = rect[2], y1 = rect[3];
     int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;  // empty when the box is off screen
     if (x0 <= x1 && y0 <= y1) {
         tx0 = (int)(x0 / 8); tx1 = (int)(x1 / 8) + 1;

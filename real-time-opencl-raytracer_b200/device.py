@@ -24,12 +24,21 @@ ABI_SYMBOLS = [
     "rt_memcpy_to_host", "rt_host_register", "rt_host_unregister", "rt_signal", "rt_shadow_device", "rt_diffuse_rays_device", "rt_render_frame_device", "rt_get_counters",
     "rt_create_group", "rt_destroy_group", "rt_group_last_error", "rt_group_size", "rt_group_context", "rt_group_upload_scene",
     "rt_group_set_params", "rt_group_set_option", "rt_render_frame_tiled", "rt_primary_tiled", "rt_group_stats",
-    "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest", "rt_selftest_range", "rt_selftest_exhaustive", "rt_tile_hint_stats", "rt_pack_scene_host", "rt_free_host",
+    "rt_reset_counters", "rt_set_option", "rt_scene_info", "rt_selftest", "rt_selftest_range", "rt_selftest_exhaustive", "rt_tile_hint_stats", "rt_cull_rect_host", "rt_pack_scene_host", "rt_free_host",
 ]
 
 
 class RtError(RuntimeError):
     pass
+
+
+def cull_rect(params, w, h):
+    """host-only: inclusive pixel rectangle (x0, x1, y0, y1) outside of which no pixel can pass the scene gate"""
+    p = np.ascontiguousarray(params, dtype=np.float32)
+    out = (C.c_int64 * 4)()
+    if lib().rt_cull_rect_host(p.ctypes.data, w, h, out):
+        raise RtError("rt_cull_rect_host: bad arguments")
+    return tuple(int(v) for v in out)
 
 
 def lib():
@@ -84,6 +93,7 @@ def lib():
         L.rt_free_host.restype = None
         L.rt_selftest_range.argtypes = [vp, i64, C.c_uint32, i32, C.POINTER(C.c_uint64)]
         L.rt_tile_hint_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.rt_cull_rect_host.argtypes = [vp, i32, i32, C.POINTER(C.c_int64)]
         L.rt_selftest_exhaustive.argtypes = [vp, C.c_uint32, C.c_uint32, i32, i32, C.c_uint32, C.POINTER(C.c_uint64)]
         L.rt_create_group.argtypes = [i32, vp, C.POINTER(vp)]
         L.rt_destroy_group.argtypes = [vp]
