@@ -69,21 +69,56 @@ def build_scene():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML, in process, once per
+    timed step right after the step's kernel has finished -- inside the region, but not while a timed kernel runs. (A
+    concurrent `nvidia-smi -lms 50` loop, the first implementation, cost the 0.2 ms kernel 3-4 %: 0.206 -> 0.213-0.217 ms,
+    tools/headline_probe.py. It is kept as the fallback when NVML cannot be loaded, at the recipe's 200 ms.)"""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.nvml, self.handle, self.first = gpu_index, [], None, None, None, 0
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+            import pynvml
+
+            pynvml.nvmlInit()
+            import torch
+
+            try:  # CUDA_VISIBLE_DEVICES may renumber the devices: go through the PCI address of torch's device
+                pr = torch.cuda.get_device_properties(self.gpu)
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+            except Exception:  # noqa: BLE001
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml = pynvml
+            self.sample()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def sample(self):
+        """one NVML sample (no-op in the nvidia-smi fallback, which polls by itself)"""
+        if not self.nvml:
+            return
+        n = self.nvml
+        try:
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            flag = lambda name: "Active" if (mask & getattr(n, name, 0)) else "Not Active"  # noqa: E731
+            self.rows.append([str(self.gpu), str(sm), str(mx), "", "", flag("nvmlClocksEventReasonHwSlowdown"),
+                              flag("nvmlClocksEventReasonHwThermalSlowdown"), flag("nvmlClocksEventReasonSwThermalSlowdown"),
+                              flag("nvmlClocksEventReasonSwPowerCap")])
+        except Exception:  # noqa: BLE001
+            pass
 
     def _read(self):
         for line in self.proc.stdout:
@@ -107,7 +142,7 @@ class ClockSampler:
                 self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows[getattr(self, "first", 0):]:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -117,7 +152,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "how": "NVML, one sample per timed step right after its kernel" if self.nvml else "nvidia-smi -lms 200 during the timed region"}
 
 
 def oracle_pass(arrays, bvh, params, w, h, repeats, threads=None):
@@ -400,6 +436,7 @@ def main():
             step()
             e1.record()
         torch.cuda.synchronize()
+        sampler.sample()
         step_ms.append(e0.elapsed_time(e1))
     barrier()
     launches = ctx.counters()["kernel_launches"]
@@ -534,11 +571,12 @@ def main():
 
     # clocks: the sampling window covers the K timed steps and the e2e loop; if the timed steps were shorter than
     # two sampling periods, extend the window with more (untimed) steps of the same load
-    with torch.cuda.stream(stream):
-        t_end = time.time() + 0.4
-        while time.time() < t_end:
-            step()
-            stream.synchronize()
+    if not sampler.nvml:  # (the nvidia-smi fallback polls every 200 ms; NVML samples were taken step by step)
+        with torch.cuda.stream(stream):
+            t_end = time.time() + 0.8
+            while time.time() < t_end:
+                step()
+                stream.synchronize()
     clocks = sampler.stop()
 
     timer = Timer(torch, stream, flush)
