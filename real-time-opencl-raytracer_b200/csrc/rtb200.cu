@@ -248,7 +248,11 @@ extern "C" int rt_destroy(rt_context* ctx) {
 
 extern "C" int rt_set_stream(rt_context* ctx, void* cuda_stream) {
     if (!ctx) return RT_E_INVALID;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    // The tile hints of one launch are read by the next launch of the same geometry; stream order is what makes that safe.
+    // On a new stream nothing orders the two, and a half-written hint buffer could hide rows from the queue: start over.
+    if (s != ctx->stream) forget_hints(ctx);
+    ctx->stream = s;
     return RT_OK;
 }
 
