@@ -457,7 +457,7 @@ __device__ __forceinline__ void store_ray(float4* rays_out, long long i, const R
 // ---- persistent-warp trace kernel ------------------------------------------------------------------
 // Grid = (resident blocks per SM) x 148 SMs; every warp pulls 32-ray batches from a global queue
 // head with one atomicAdd by lane 0 + a shuffle, until the queue is empty.
-template <int SRC, bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX = false>
+template <int SRC, bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX = false, bool INNER_EXIT = false>
 __global__ void __launch_bounds__(kBlockThreads, (SRC == SRC_PRIMARY && !FAST_BOX) ? RTB_MINB_PRIMARY : RTB_MINB_BATCH) trace_kernel(const TraceArgs a, int smem_count) {
     extern __shared__ float4 smem_pairs[];
     if (SMEM_TOP) {
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(kBlockThreads, (SRC == SRC_PRIMARY && !FAST_BO
         }
         if (active) {
             traced++;
-            const TraceResult r = traverse<ANY_HIT, SMEM_TOP, FAST_BOX>(a.scene, smem_pairs, smem_count, ray, tmax);
+            const TraceResult r = traverse<ANY_HIT, SMEM_TOP, FAST_BOX, INNER_EXIT>(a.scene, smem_pairs, smem_count, ray, tmax);
             if (SRC != SRC_PRIMARY || a.hits_out) a.hits_out[out_index] = make_float4(__int_as_float(r.idx), r.t, r.u, r.v);
             if (SRC == SRC_PRIMARY && a.frame_out) pixel_sink(a)[out_index] = (unsigned int)r.idx;
         }
@@ -564,6 +564,7 @@ __global__ void __launch_bounds__(kBlockThreads, (SRC == SRC_PRIMARY && !FAST_BO
 // over 8 GPUs. Outputs (each optional): the closest-hit records, the shadow any-hit records, and the 4-byte/pixel
 // visibility word  vis = -1 (no hit)  |  3*triId + (occluded ? 1 : 0)  with the reference's rule
 // occluded = shadow idx >= 0 && shadow t > 0.025 (vR.cl:1444-1449); 3*triId is a multiple of 3, so the word is lossless.
+template <bool INNER_EXIT>
 __global__ void __launch_bounds__(kBlockThreads) primary_shadow_kernel(const TraceArgs a) {
     const int lane = threadIdx.x & 31;
     const f3 light_pos = ld3(a.params.light_pos);
@@ -593,12 +594,12 @@ __global__ void __launch_bounds__(kBlockThreads) primary_shadow_kernel(const Tra
             if (!certainly_gated_out(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h) &&
                 primary_ray(a.params, (unsigned)x, (unsigned)y, (unsigned)a.w, (unsigned)a.h, ray)) {
                 traced++;
-                hit = traverse<false, false>(a.scene, nullptr, 0, ray, RTB_T_INIT);
+                hit = traverse<false, false, false, INNER_EXIT>(a.scene, nullptr, 0, ray, RTB_T_INIT);
                 if (hit.idx >= 0) {
                     traced++;
                     f3 hp;
                     const Ray sray = shadow_ray(light_pos, ray, hit.t, hp);
-                    sh = traverse<true, false>(a.scene, nullptr, 0, sray, RTB_T_INIT);
+                    sh = traverse<true, false, false, INNER_EXIT>(a.scene, nullptr, 0, sray, RTB_T_INIT);
                 }
             }
             if (a.hits_out) a.hits_out[px] = make_float4(__int_as_float(hit.idx), hit.t, hit.u, hit.v);
@@ -723,7 +724,7 @@ __device__ __forceinline__ unsigned int resolve_pixel(f3 color, float shadow_coe
     return rgb_to_int(color.x * 255, color.y * 255, color.z * 255);
 }
 
-template <bool SMEM_TOP>
+template <bool SMEM_TOP, bool INNER_EXIT>
 __device__ __forceinline__ unsigned int render_pixel(const TraceArgs& a, const float4* smem_pairs, int smem_count, unsigned x,
                                                      unsigned y, unsigned int& traced) {
     const SceneView& s = a.scene;
@@ -737,14 +738,14 @@ __device__ __forceinline__ unsigned int render_pixel(const TraceArgs& a, const f
 
     while (continue_path && ray_depth < RTB_RAY_TRACE_DEPTH) {
         traced++;
-        const TraceResult hit = traverse<false, SMEM_TOP>(s, smem_pairs, smem_count, r, RTB_T_INIT);
+        const TraceResult hit = traverse<false, SMEM_TOP, false, INNER_EXIT>(s, smem_pairs, smem_count, r, RTB_T_INIT);
         float shadow_coef = 1.0f;
         if (hit.idx >= 0) {
             ray_depth++;
             traced++;
             const PathVertex pv = shade_path_vertex(s, light_pos, r, hit.idx, hit.t);
             {
-                const TraceResult sh = traverse<true, SMEM_TOP>(s, smem_pairs, smem_count, pv.shadow, RTB_T_INIT);
+                const TraceResult sh = traverse<true, SMEM_TOP, false, INNER_EXIT>(s, smem_pairs, smem_count, pv.shadow, RTB_T_INIT);
                 if (sh.idx >= 0 && sh.t > 0.025f) shadow_coef = 0.25f;
             }
             color = add3(color, pv.rez_color);
@@ -757,7 +758,7 @@ __device__ __forceinline__ unsigned int render_pixel(const TraceArgs& a, const f
     return resolve_pixel(color, shadow_coef_sum, ray_depth);
 }
 
-template <bool SMEM_TOP>
+template <bool SMEM_TOP, bool INNER_EXIT = false>
 __global__ void __launch_bounds__(kBlockThreads, 8) render_kernel(const TraceArgs a, int smem_count) {
     extern __shared__ float4 smem_pairs[];
     if (SMEM_TOP) {
@@ -782,7 +783,7 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_kernel(const TraceArg
         long long k;
         tile_pixel(a, batch, lane, x, y, tx, k);
         if (x < a.w && y < a.h && ((tw.rows >> (lane >> 3)) & 1u))
-            pixel_sink(a)[(size_t)y * a.w + x] = render_pixel<SMEM_TOP>(a, smem_pairs, smem_count, (unsigned)x, (unsigned)y, traced);
+            pixel_sink(a)[(size_t)y * a.w + x] = render_pixel<SMEM_TOP, INNER_EXIT>(a, smem_pairs, smem_count, (unsigned)x, (unsigned)y, traced);
         finish_tile(a, tx, k, y - (lane >> 3), lane, __popc(tw.rows));
         __syncwarp();
         record_tile(a, s_sched, lane, tw);

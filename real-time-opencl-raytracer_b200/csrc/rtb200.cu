@@ -80,6 +80,9 @@ struct rt_context {
     int opt_store_group = -1;   // row assembly of 4-byte/pixel frames: -1 = auto (on when the frame is host or peer memory),
                                 // 0 = off, 2 = groups of 4 tiles (128-byte rows), 4 = groups of 16 tiles (512-byte rows)
     int opt_l2_persist_kb = 0;  // experiment: L2 persisting access window over the first N KB of the node pairs (the BFS-ordered top)
+    int opt_batch_inner_exit = -1;  // batch kernels: early exit from the inner loop (traverse.cuh INNER_EXIT): -1 = when the scene's
+                                // traversal data (node pairs + triangles) does not fit L2, 0 = never, 1 = always
+    size_t l2_bytes = 0;
     int opt_gate_cull = 1;      // camera-ray kernels: tiles outside the scene box's screen rectangle leave the queue (cull_setup)
     int opt_tile_hints = 1;     // temporal tile scheduling of the camera-ray kernels (kernels.cuh "tile scheduler")
     int opt_hint_heavy_pct = 12;                        // the slowest N percent of the tiles start first
@@ -156,6 +159,7 @@ static int init_context(rt_context* ctx, int device_ordinal) {
     if (!scope.ok) return set_err(nullptr, RT_E_CUDA, "cudaSetDevice(%d) failed", device_ordinal);
     cudaDeviceProp prop;
     CK(nullptr, cudaGetDeviceProperties(&prop, device_ordinal));
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
     ctx->num_sms = prop.multiProcessorCount;
     CK(nullptr, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
@@ -434,6 +438,7 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
     else if (!strcmp(name, "store_group")) ctx->opt_store_group = (value == 0 || value == 2 || value == 4) ? value : -1;
     else if (!strcmp(name, "l2_persist_kb")) { ctx->opt_l2_persist_kb = value < 0 ? 0 : value; return apply_l2_window(ctx); }
     else if (!strcmp(name, "gate_cull")) ctx->opt_gate_cull = value ? 1 : 0;
+    else if (!strcmp(name, "inner_exit_batch")) ctx->opt_batch_inner_exit = value < 0 ? -1 : (value ? 1 : 0);
     else if (!strcmp(name, "tile_hints")) { ctx->opt_tile_hints = value ? 1 : 0; forget_hints(ctx); }
     else if (!strcmp(name, "hint_heavy_pct")) { ctx->opt_hint_heavy_pct = value < 1 ? 1 : value; forget_hints(ctx); }
     else if (!strcmp(name, "hint_light_pct")) { ctx->opt_hint_light_pct = value < 0 ? -1 : (value > 90 ? 90 : value); forget_hints(ctx); }
@@ -822,6 +827,13 @@ static int smem_top_count(const rt_context* ctx) {
     return c;
 }
 
+// Which instance of the batch kernels' traversal loop: see traverse.cuh INNER_EXIT.
+static bool inner_exit_for(const rt_context* ctx) {
+    if (ctx->opt_batch_inner_exit >= 0) return ctx->opt_batch_inner_exit != 0;
+    const size_t traversal_bytes = 64 * (size_t)ctx->hdr.num_pairs + 48 * ((size_t)ctx->hdr.num_tris + 1);
+    return ctx->l2_bytes && traversal_bytes > ctx->l2_bytes;
+}
+
 static int require(rt_context* ctx, bool params, bool shading) {
     if (!ctx) return RT_E_INVALID;
     if (!ctx->have_scene) return set_err(ctx, RT_E_NO_SCENE, "no scene uploaded (rt_upload_scene / rt_adopt_scene_blob)");
@@ -874,10 +886,12 @@ static int do_trace_device(rt_context* ctx, int mode, long long n, const rt_ray*
         rc = launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false, true>, a, 0);
     else if (mode == RT_CLOSEST)
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, true>, a, st)
-                : launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false>, a, 0);
+                : inner_exit_for(ctx) ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false, false, true>, a, 0)
+                                      : launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false>, a, 0);
     else
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, true>, a, st)
-                : launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, false>, a, 0);
+                : inner_exit_for(ctx) ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, false, false, true>, a, 0)
+                                      : launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, false>, a, 0);
     return rc;
 }
 
@@ -1016,7 +1030,8 @@ static int primary_impl(rt_context* ctx, int w, int h, int part, int n_parts, in
         rc = launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false, true>, a, 0, nullptr, counter, zero_bytes);
     else
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, true>, a, st, nullptr, counter, zero_bytes)
-                : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0, nullptr, counter, zero_bytes);
+                : inner_exit_for(ctx) ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false, false, true>, a, 0, nullptr, counter, zero_bytes)
+                                      : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0, nullptr, counter, zero_bytes);
     commit_hints(hs, rc);
     return rc;
 }
@@ -1041,7 +1056,8 @@ static int primary_shadow_impl(rt_context* ctx, int w, int h, int part, int n_pa
     cull_setup(ctx, a);
     rt_context::HintSlot* hs = nullptr;
     if ((rc = attach_hints(ctx, HINT_KIND_PRIMARY_SHADOW, a, -1, nullptr, &hs, &counter, &zero_bytes))) return rc;
-    rc = launch_persistent(ctx, primary_shadow_kernel, a, (size_t)0, nullptr, counter, zero_bytes);
+    rc = inner_exit_for(ctx) ? launch_persistent(ctx, primary_shadow_kernel<true>, a, (size_t)0, nullptr, counter, zero_bytes)
+                             : launch_persistent(ctx, primary_shadow_kernel<false>, a, (size_t)0, nullptr, counter, zero_bytes);
     commit_hints(hs, rc);
     return rc;
 }
@@ -1223,7 +1239,8 @@ extern "C" int rt_shadow_device(rt_context* ctx, int64_t n, const rt_ray* d_rays
         rc = launch_lanes(ctx, trace_lanes_kernel<SRC_SHADOW, true>, a, n);
     else
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, true>, a, st)
-                : launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, false>, a, 0);
+                : inner_exit_for(ctx) ? launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, false, false, true>, a, 0)
+                                      : launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, false>, a, 0);
     return rc;
 }
 
@@ -1280,7 +1297,8 @@ static int render_frame_impl(rt_context* ctx, int w, int h, int part, int n_part
     rt_context::HintSlot* hs = nullptr;
     if ((rc = attach_hints(ctx, HINT_KIND_FRAME, a, slot, stream, &hs, &counter, &zero_bytes))) return rc;
     rc = st ? launch_persistent(ctx, render_kernel<true>, a, st, stream, counter, zero_bytes)
-            : launch_persistent(ctx, render_kernel<false>, a, 0, stream, counter, zero_bytes);
+            : inner_exit_for(ctx) ? launch_persistent(ctx, render_kernel<false, true>, a, 0, stream, counter, zero_bytes)
+                                  : launch_persistent(ctx, render_kernel<false>, a, 0, stream, counter, zero_bytes);
     commit_hints(hs, rc);
     return rc;
 }

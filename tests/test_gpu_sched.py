@@ -220,3 +220,50 @@ def test_culled_queue_follows_a_moving_camera(ctx):
         ctx.set_option("tile_hints", 1)
         for k, v in (("hint_heavy_pct", 12), ("hint_split_pct", 80), ("hint_keep_pct", 30)):
             ctx.set_option(k, v)
+
+
+def test_inner_exit_instances_give_identical_results(ctx):
+    """the batch kernels exist in two instances of the traversal loop (traverse.cuh INNER_EXIT: leave the inner loop early
+    while others wait on a leaf; picked per scene by its size against L2). Forcing either on the same scene must not change
+    one bit of any entry point: rays from buffers (closest / any), camera rays, shadow rays, the fused pass, frames."""
+    import torch
+
+    g = load_scene("mix")
+    ctx.upload_scene(mesh_dict(g), g["ref_nodes"], g["ref_tri_indices"])
+    w, h = 328, 204
+    params, _ = rtb200.camera_params(w, h, g["aabb_min"], g["aabb_max"], light_pos=GRAZING)
+    ctx.set_params(params)
+    n = w * h
+    ctx.set_option("scheduler", 0)  # the batch kernels (ray buffers default to the lanes kernel)
+
+    def run_all():
+        hits = torch.zeros((n, 4), device="cuda")
+        rays = torch.zeros((n, 8), device="cuda")
+        sh = torch.zeros((n, 4), device="cuda")
+        anyh = torch.zeros((n, 4), device="cuda")
+        clo = torch.zeros((n, 4), device="cuda")
+        vis = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+        img = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+        ctx.primary_device(w, h, hits, rays)
+        ctx.shadow_device(n, rays, hits, sh)
+        ctx.trace_device(rtb200.ANY, n, rays, anyh)
+        ctx.trace_device(rtb200.CLOSEST, n, rays, clo)
+        ctx.primary_shadow_device(w, h, None, None, vis)
+        ctx.render_frame_device(w, h, img)
+        ctx.synchronize()
+        return [t.cpu().numpy().copy() for t in (hits, sh, anyh, clo, vis, img)]
+
+    try:
+        ctx.set_option("inner_exit_batch", 0)
+        want = run_all()
+        ctx.set_option("inner_exit_batch", 1)
+        for _ in range(3):
+            got = run_all()
+            for name, a, b in zip(("primary", "shadow", "any-hit buffer", "closest buffer", "visibility frame", "shaded frame"), got, want):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{name} differs between the two loop instances"
+        golden = g["random_hits_closest"].view(HIT).reshape(-1)
+        from conftest import assert_hits_identical
+        assert_hits_identical(ctx.trace(rtb200.CLOSEST, g["random_rays"]), golden, "INNER_EXIT instance vs golden")
+    finally:
+        ctx.set_option("inner_exit_batch", -1)
+        ctx.set_option("scheduler", -1)

@@ -50,7 +50,9 @@ def test_packed_box_test_is_emitted_as_written(sass):
         ops = sass[n]
         a, m, f = ops["FADD2"], ops["FMUL2"], ops["FFMA2"]
         if a == 0 and m == 0 and f == 0:
-            assert "ELb1EEEvNS_9TraceArgsEi" in n and "trace_kernel" in n, f"{n}: no packed box test"  # FAST_BOX instances only
+            # only the FAST_BOX instances (4th boolean of trace_kernel<SRC, ANY_HIT, SMEM_TOP, FAST_BOX, INNER_EXIT>) have no packed test
+            args = re.search(r"trace_kernelILi\dELb([01])ELb([01])ELb([01])ELb([01])EE", n)
+            assert args and args.group(3) == "1", f"{n}: no packed box test"
             continue
         packed += 1
         assert a == m and f == 2 * a and a % 6 == 0, f"{n}: FADD2 {a} FMUL2 {m} FFMA2 {f}"
