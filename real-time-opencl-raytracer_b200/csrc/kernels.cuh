@@ -56,6 +56,8 @@ struct TraceArgs {
     // a tile row) write the miss values of everything outside. n_fill == 0: no culling, the rectangle is the whole frame.
     int in_tx0, in_tx1, in_k0, in_k1;
     unsigned int n_fill;
+    int fill_first;  // the fill items lead the queue instead of closing it (frames stored straight into host memory: their
+                     // burst of stores then overlaps the slow tiles' tracing instead of trailing the launch)
     // Temporal tile scheduling (camera-ray kernels; see "tile scheduler" below): what the previous launch of this frame
     // geometry learnt about its tiles, and where this launch records the same for the next one. Either may be NULL.
     const unsigned int* hint_in;
@@ -333,6 +335,14 @@ __device__ __forceinline__ bool next_tile(const TraceArgs& a, const unsigned int
             i = __shfl_sync(0xffffffffu, (unsigned int)i, 0);
         }
         tw.t0 = (unsigned int)clock();
+        if (a.fill_first) {
+            if (i < a.n_fill) {
+                tw.batch = (long long)i;
+                tw.rows = kFillItem;
+                return true;
+            }
+            i -= a.n_fill;
+        }
         const unsigned long long n_split = s_sched[0], n_heavy = s_sched[1];
         if (i < n_split) {
             // both lists were appended in completion order, i.e. roughly shortest first: walk them backwards (longest first)
@@ -357,7 +367,7 @@ __device__ __forceinline__ bool next_tile(const TraceArgs& a, const unsigned int
             const unsigned long long n_light = s_sched[6];
             if (i >= n_light) {  // and last the store-only items for what lies outside the scene box's rectangle
                 i -= n_light;
-                if (i >= a.n_fill) return false;
+                if (a.fill_first || i >= a.n_fill) return false;
                 tw.batch = (long long)i;
                 tw.rows = kFillItem;
                 return true;

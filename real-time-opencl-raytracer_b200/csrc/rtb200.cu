@@ -641,7 +641,7 @@ extern "C" int rt_cull_rect_host(const float params[32], int w, int h, int64_t o
     return RT_OK;
 }
 
-static void cull_setup(const rt_context* ctx, TraceArgs& a) {
+static void cull_setup(const rt_context* ctx, TraceArgs& a, bool frame_kernel = false) {
     const int tile_rows_total = (a.h + 3) / 4;
     const long long K = a.tiles_x ? a.num_batches / a.tiles_x : 0;  // this rank's tile rows
     a.in_tx0 = 0;
@@ -651,7 +651,11 @@ static void cull_setup(const rt_context* ctx, TraceArgs& a) {
     a.n_fill = 0;
     // (a pass that stores straight into host memory is paced by PCIe and wants its stores -- two thirds of them miss records
     // -- spread over the launch, not bunched in fill items at the end: it keeps the plain enumeration, like it keeps the plain queue)
-    if (!ctx->opt_gate_cull || a.rays_out || a.tile_order != 0 || K < 1 || stores_to_host_memory(a)) return;
+    // The shaded frame is the exception: 4 bytes per pixel behind 0.7 ms of tracing are far from the link's limit, so it is
+    // culled too, with the fill items FIRST -- their burst of (black) pixels crosses PCIe while the slow tiles trace.
+    const bool host_sink = stores_to_host_memory(a);
+    a.fill_first = (host_sink && frame_kernel) ? 1 : 0;
+    if (!ctx->opt_gate_cull || a.rays_out || a.tile_order != 0 || K < 1 || (host_sink && !frame_kernel)) return;
     long long rect[4];
     if (!cull_pixel_rect(a.params, a.w, a.h, rect)) return;
     const long long x0 = rect[0], x1 = rect[1], y0 = rect[2], y1 = rect[3];
@@ -703,7 +707,7 @@ static int attach_hints(rt_context* ctx, int kind, TraceArgs& a, int frame_slot,
     // A pass that stores straight into host memory is paced by the PCIe link, which wants the stores spread evenly over
     // the launch; starting the slow tiles first and ending on the quick ones bunches the stores at the end (measured:
     // rt_primary into pinned memory 0.71 -> 0.78 ms). Such passes keep the plain row-major queue.
-    if (stores_to_host_memory(a)) return RT_OK;
+    if (kind != HINT_KIND_FRAME && stores_to_host_memory(a)) return RT_OK;
     rt_context::HintSlot* hs = nullptr;
     rt_context::HintSlot* lru = &ctx->hint_slots[0];
     for (auto& c : ctx->hint_slots) {
@@ -1293,7 +1297,7 @@ static int render_frame_impl(rt_context* ctx, int w, int h, int part, int n_part
     size_t zero_bytes = sizeof(unsigned long long);
     if ((rc = frame_sink(ctx, a, d_out, slot >= 0 ? ctx->slots[slot].rowasm : ctx->rowasm, &counter, &zero_bytes))) return rc;
     const int st = smem_top_count(ctx);
-    cull_setup(ctx, a);
+    cull_setup(ctx, a, true);
     rt_context::HintSlot* hs = nullptr;
     if ((rc = attach_hints(ctx, HINT_KIND_FRAME, a, slot, stream, &hs, &counter, &zero_bytes))) return rc;
     rc = st ? launch_persistent(ctx, render_kernel<true>, a, st, stream, counter, zero_bytes)
