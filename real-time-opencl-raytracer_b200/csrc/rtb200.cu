@@ -760,7 +760,11 @@ static void commit_hints(rt_context::HintSlot* hs, int rc) {
 // Destination of a pass's 4-byte/pixel frame. Decides whether rows are assembled (TraceArgs::stage): always when the
 // `store_group` option says so; in auto mode when `dst` is page-locked host memory or memory of another GPU, where a
 // tile's 32-byte row pieces would travel as quarter-filled PCIe / NVLink writes. Local frames are stored directly.
-static int frame_sink(rt_context* ctx, TraceArgs& a, void* dst, rt_context::RowAsm& ra, unsigned long long** counter, size_t* zero_bytes) {
+// `long_kernel`: the pass is the shaded frame (0.7 ms of tracing behind 4 bytes per pixel) -- alone on its link it gains nothing
+// from assembled rows and pays for the group hand-shake (measured 0.757 vs 0.788 ms into pinned memory), so auto mode assembles
+// its host frames only when several GPUs share the host's write bandwidth (n_parts > 1).
+static int frame_sink(rt_context* ctx, TraceArgs& a, void* dst, rt_context::RowAsm& ra, unsigned long long** counter, size_t* zero_bytes,
+                      bool long_kernel = false) {
     a.frame_out = (unsigned int*)dst;
     a.group_log2 = 0;
     if (!dst) return RT_OK;
@@ -770,7 +774,7 @@ static int frame_sink(rt_context* ctx, TraceArgs& a, void* dst, rt_context::RowA
         memset(&attr, 0, sizeof attr);
         mode = 0;
         if (cudaPointerGetAttributes(&attr, dst) == cudaSuccess) {
-            if (attr.type == cudaMemoryTypeHost) mode = 4;
+            if (attr.type == cudaMemoryTypeHost) mode = (long_kernel && a.n_parts == 1) ? 0 : 4;
             else if (attr.type == cudaMemoryTypeDevice && attr.device != ctx->device) mode = 2;
         } else {
             cudaGetLastError();
@@ -1295,7 +1299,7 @@ static int render_frame_impl(rt_context* ctx, int w, int h, int part, int n_part
     cudaStream_t stream = slot >= 0 ? ctx->slots[slot].stream : nullptr;
     unsigned long long* counter = slot >= 0 ? ctx->d_counter + 1 + slot : nullptr;
     size_t zero_bytes = sizeof(unsigned long long);
-    if ((rc = frame_sink(ctx, a, d_out, slot >= 0 ? ctx->slots[slot].rowasm : ctx->rowasm, &counter, &zero_bytes))) return rc;
+    if ((rc = frame_sink(ctx, a, d_out, slot >= 0 ? ctx->slots[slot].rowasm : ctx->rowasm, &counter, &zero_bytes, true))) return rc;
     const int st = smem_top_count(ctx);
     cull_setup(ctx, a, true);
     rt_context::HintSlot* hs = nullptr;
