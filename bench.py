@@ -409,12 +409,18 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    with torch.cuda.stream(stream):
-        for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3)):  # warm-up steps run like the timed ones (L2 flushed before each): the tile hints a
+        if flush is not None:               # launch records are then those of the conditions that are timed
+            flush.fill_(1)
+            torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
             step()
     barrier()
     # rays per step = traversals the kernels start (their own counter), summed over ranks
     ctx.reset_counters()
+    if flush is not None:
+        flush.fill_(1)
+        torch.cuda.synchronize()
     with torch.cuda.stream(stream):
         step()
     rays_total = allsum(ctx.counters()["rays_traced"])
@@ -606,6 +612,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_string(w, h), "frame": [w, h], "rays_per_step": rays_total, "pixels_per_step": n_pix,
                        "mpixels_per_s": n_pix * args.steps / (total_ms * 1e-3) / 1e6, "l2": "not flushed" if args.no_flush else "flushed between timed steps (256 MiB fill)",
+                       "step_ms_min_median_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
+                       "tile_scheduler": "temporal tile hints + scene-box culling of the tile queue (DESIGN 3.6); warm-up steps run under the timed conditions",
                        "scene_build_s": build_s, "scene_broadcast_ms": bcast_ms, "scene_blob_bytes": blob_bytes,
                        "scene_broadcast": "n/a (1 GPU)" if world == 1 else "one NCCL broadcast of the packed scene buffer, timed alone with CUDA events (max over ranks)",
                        "partition": "n/a (1 GPU)" if world == 1 else f"interleaved {BAND_ROWS}-row bands, one process per GPU",
