@@ -238,7 +238,6 @@ __device__ __forceinline__ void finish_tile(const TraceArgs& a, int tx, long lon
 //   * the launch's span (longest life of a persistent warp), per tile the time it took (SM clock) and a histogram of those
 //     times. The slowest `heavy_pct` percent of the tiles go on the HEAVY list; a tile that took more than `split_pct`
 //     percent of the previous launch's span -- one that by itself decides when the launch ends -- goes on the SPLIT list
-//     as four one-row (8x1 pixel) items
 //     as four one-row (8x1 pixel) items; the quickest `light_pct` percent (of the tiles that traced at all) go on the
 //     LIGHT list
 //   * the next launch's queue is [split rows][heavy tiles][all tiles in row-major order, minus what the lists cover]
