@@ -308,28 +308,50 @@ extern "C" int rt_group_upload_scene(rt_group* g, const float* verts, int V, con
             }
         if (p >= 0) cudaSetDevice(p);
     };
+    // on a failure before the new blobs are adopted the contexts still borrow the old ones: put those back and drop the new
+    std::vector<bool> swapped(g->n, false);
+    auto abandon_new = [&]() {
+        int p = -1;
+        cudaGetDevice(&p);
+        for (int r = 1; r < g->n; r++)
+            if (swapped[r]) {
+                cudaSetDevice(g->dev[r]);
+                cudaStreamSynchronize(g->stream[r]);  // a collective may still be writing into it
+                cudaFree(g->d_blob[r]);
+                g->d_blob[r] = old_blob[r];
+                old_blob[r] = nullptr;
+                swapped[r] = false;
+            }
+        if (p >= 0) cudaSetDevice(p);
+    };
     for (int r = 1; r < g->n; r++) {
         cudaSetDevice(g->dev[r]);
         rt_synchronize(g->ctx[r]);
         void* fresh = nullptr;
         if (cudaMalloc(&fresh, bytes) != cudaSuccess) {
             if (prev >= 0) cudaSetDevice(prev);
+            abandon_new();
             return gerr(g, RT_E_CUDA, "cudaMalloc(%zu) for the scene blob failed on GPU %d", bytes, g->dev[r]);
         }
         old_blob[r] = g->d_blob[r];
         g->d_blob[r] = fresh;
+        swapped[r] = true;
     }
     if (prev >= 0) cudaSetDevice(prev);
     rt_synchronize(g->ctx[0]);
     const auto t0 = std::chrono::steady_clock::now();
     if (g->broadcast_mode == 0) {
         std::lock_guard<std::mutex> lk(g_nccl_mutex);
-        if (!g_nccl.load()) return gerr(g, RT_E_CUDA, "%s; set group option \"broadcast\" = 1 for peer copies", g_nccl.problem.c_str());
+        if (!g_nccl.load()) {
+            abandon_new();
+            return gerr(g, RT_E_CUDA, "%s; set group option \"broadcast\" = 1 for peer copies", g_nccl.problem.c_str());
+        }
         if (g->comms.empty()) {
             g->comms.assign(g->n, nullptr);
             const ncclResult_t e = g_nccl.CommInitAll(g->comms.data(), g->n, g->dev.data());
             if (e != ncclSuccess) {
                 g->comms.clear();
+                abandon_new();
                 return gerr(g, RT_E_CUDA, "ncclCommInitAll failed: %s", g_nccl.GetErrorString(e));
             }
         }
@@ -345,15 +367,23 @@ extern "C" int rt_group_upload_scene(rt_group* g, const float* verts, int V, con
         if (e == ncclSuccess) e = e2;
         cudaEventRecord(g->ev1[0], g->stream[0]);
         if (prev >= 0) cudaSetDevice(prev);
-        if (e != ncclSuccess) return gerr(g, RT_E_CUDA, "ncclBroadcast failed: %s", g_nccl.GetErrorString(e));
+        if (e != ncclSuccess) {
+            abandon_new();
+            return gerr(g, RT_E_CUDA, "ncclBroadcast failed: %s", g_nccl.GetErrorString(e));
+        }
     } else {
-        if ((rc = enable_peers(g))) return rc;
+        if ((rc = enable_peers(g))) {
+            abandon_new();
+            return rc;
+        }
         cudaGetDevice(&prev);
         cudaSetDevice(g->dev[0]);
         cudaEventRecord(g->ev0[0], g->stream[0]);
         for (int r = 1; r < g->n; r++)
             if (cudaMemcpyPeerAsync(g->d_blob[r], g->dev[r], blob0, g->dev[0], bytes, g->stream[0]) != cudaSuccess) {
+                cudaStreamSynchronize(g->stream[0]);
                 if (prev >= 0) cudaSetDevice(prev);
+                abandon_new();
                 return gerr(g, RT_E_CUDA, "cudaMemcpyPeerAsync to GPU %d failed", g->dev[r]);
             }
         cudaEventRecord(g->ev1[0], g->stream[0]);
@@ -364,7 +394,10 @@ extern "C" int rt_group_upload_scene(rt_group* g, const float* verts, int V, con
     cudaSetDevice(g->dev[0]);
     const cudaError_t sync0 = cudaStreamSynchronize(g->stream[0]);
     if (prev >= 0) cudaSetDevice(prev);
-    if (sync0 != cudaSuccess) return gerr(g, RT_E_CUDA, "scene broadcast failed on GPU %d: %s", g->dev[0], cudaGetErrorString(sync0));
+    if (sync0 != cudaSuccess) {
+        abandon_new();
+        return gerr(g, RT_E_CUDA, "scene broadcast failed on GPU %d: %s", g->dev[0], cudaGetErrorString(sync0));
+    }
     rc = run_all(g, [g, bytes](int r) {
         if (cudaStreamSynchronize(g->stream[r]) != cudaSuccess) return (int)RT_E_CUDA;
         return r == 0 ? (int)RT_OK : rt_adopt_scene_blob(g->ctx[r], g->d_blob[r], bytes);
