@@ -75,8 +75,8 @@ __device__ __forceinline__ TraceResult traverse_impl(const SceneView& s, const f
                 q0 = p[0]; q1 = p[1]; q2 = p[2]; q3 = p[3];
             } else {
                 const float4* p = s.pairs + 4 * (size_t)cur;
-                ldg256(p, q0, q1);
-                ldg256(p + 2, q2, q3);
+                ldg256<INNER_EXIT>(p, q0, q1);
+                ldg256<INNER_EXIT>(p + 2, q2, q3);
             }
             float t0n, t0f, t1n, t1f;
             if (FAST_BOX) {
