@@ -19,7 +19,8 @@ namespace rtb {
 
 static constexpr int kLaneChunk = 32;   // work items a warp takes from the global queue per atomicAdd
 
-template <int SRC, bool ANY_HIT>
+// WIDE_L2: the node loads ask L2 for 256-byte fills (device_math.cuh ldg256): the instance for scenes that do not fit L2.
+template <int SRC, bool ANY_HIT, bool WIDE_L2 = false>
 __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_kernel(const TraceArgs a, int refill_threshold, int inner_exit_threshold) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -137,8 +138,8 @@ __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_ker
             if (inner) {
                 const float4* p = a.scene.pairs + 4 * (size_t)cur;
                 float4 q0, q1, q2, q3;
-                ldg256(p, q0, q1);
-                ldg256(p + 2, q2, q3);
+                ldg256<WIDE_L2>(p, q0, q1);
+                ldg256<WIDE_L2>(p + 2, q2, q3);
                 float t0n, t0f, t1n, t1f;
                 if (warp_hoisted || rx.fast) {  // warp_hoisted is uniform: no divergent branch in the common case
                     ray_box_hoisted(rx, q0, q1, t0n, t0f);

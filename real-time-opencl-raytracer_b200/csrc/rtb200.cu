@@ -835,8 +835,9 @@ static int smem_top_count(const rt_context* ctx) {
     return c;
 }
 
-// Which instance of the batch kernels' traversal loop: see traverse.cuh INNER_EXIT.
-static bool inner_exit_for(const rt_context* ctx) {
+// Which instances of the traversal kernels run: the ones for scenes whose traversal data does not fit L2 (batch kernels:
+// early exit from the inner loop, traverse.cuh INNER_EXIT; all of them: 256-byte L2 fills on node loads) or the plain ones.
+static bool big_scene_instances(const rt_context* ctx) {
     if (ctx->opt_batch_inner_exit >= 0) return ctx->opt_batch_inner_exit != 0;
     const size_t traversal_bytes = 64 * (size_t)ctx->hdr.num_pairs + 48 * ((size_t)ctx->hdr.num_tris + 1);
     return ctx->l2_bytes && traversal_bytes > ctx->l2_bytes;
@@ -888,17 +889,17 @@ static int do_trace_device(rt_context* ctx, int mode, long long n, const rt_ray*
     const int st = smem_top_count(ctx);
     int rc;
     if (ctx->opt_scheduler != 0 && !st)
-        rc = mode == RT_CLOSEST ? launch_lanes(ctx, trace_lanes_kernel<SRC_BUFFER, false>, a, n)
-                                : launch_lanes(ctx, trace_lanes_kernel<SRC_BUFFER, true>, a, n);
+        rc = mode == RT_CLOSEST ? (big_scene_instances(ctx) ? launch_lanes(ctx, trace_lanes_kernel<SRC_BUFFER, false, true>, a, n) : launch_lanes(ctx, trace_lanes_kernel<SRC_BUFFER, false>, a, n))
+                                : (big_scene_instances(ctx) ? launch_lanes(ctx, trace_lanes_kernel<SRC_BUFFER, true, true>, a, n) : launch_lanes(ctx, trace_lanes_kernel<SRC_BUFFER, true>, a, n));
     else if (mode == RT_CLOSEST && ctx->opt_fast_box && !st)
         rc = launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false, true>, a, 0);
     else if (mode == RT_CLOSEST)
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, true>, a, st)
-                : inner_exit_for(ctx) ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false, false, true>, a, 0)
+                : big_scene_instances(ctx) ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false, false, true>, a, 0)
                                       : launch_persistent(ctx, trace_kernel<SRC_BUFFER, false, false>, a, 0);
     else
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, true>, a, st)
-                : inner_exit_for(ctx) ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, false, false, true>, a, 0)
+                : big_scene_instances(ctx) ? launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, false, false, true>, a, 0)
                                       : launch_persistent(ctx, trace_kernel<SRC_BUFFER, true, false>, a, 0);
     return rc;
 }
@@ -1030,7 +1031,7 @@ static int primary_impl(rt_context* ctx, int w, int h, int part, int n_parts, in
     if ((rc = frame_sink(ctx, a, d_idx_frame, ctx->rowasm, &counter, &zero_bytes))) return rc;
     const int st = smem_top_count(ctx);
     if (ctx->opt_scheduler == 1 && !st && d_hits && !d_idx_frame)
-        return launch_lanes(ctx, trace_lanes_kernel<SRC_PRIMARY, false>, a, a.num_batches * 32);
+        return (big_scene_instances(ctx) ? launch_lanes(ctx, trace_lanes_kernel<SRC_PRIMARY, false, true>, a, a.num_batches * 32) : launch_lanes(ctx, trace_lanes_kernel<SRC_PRIMARY, false>, a, a.num_batches * 32));
     cull_setup(ctx, a);
     rt_context::HintSlot* hs = nullptr;
     if ((rc = attach_hints(ctx, HINT_KIND_PRIMARY, a, -1, nullptr, &hs, &counter, &zero_bytes))) return rc;
@@ -1038,7 +1039,7 @@ static int primary_impl(rt_context* ctx, int w, int h, int part, int n_parts, in
         rc = launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false, true>, a, 0, nullptr, counter, zero_bytes);
     else
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, true>, a, st, nullptr, counter, zero_bytes)
-                : inner_exit_for(ctx) ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false, false, true>, a, 0, nullptr, counter, zero_bytes)
+                : big_scene_instances(ctx) ? launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false, false, true>, a, 0, nullptr, counter, zero_bytes)
                                       : launch_persistent(ctx, trace_kernel<SRC_PRIMARY, false, false>, a, 0, nullptr, counter, zero_bytes);
     commit_hints(hs, rc);
     return rc;
@@ -1064,7 +1065,7 @@ static int primary_shadow_impl(rt_context* ctx, int w, int h, int part, int n_pa
     cull_setup(ctx, a);
     rt_context::HintSlot* hs = nullptr;
     if ((rc = attach_hints(ctx, HINT_KIND_PRIMARY_SHADOW, a, -1, nullptr, &hs, &counter, &zero_bytes))) return rc;
-    rc = inner_exit_for(ctx) ? launch_persistent(ctx, primary_shadow_kernel<true>, a, (size_t)0, nullptr, counter, zero_bytes)
+    rc = big_scene_instances(ctx) ? launch_persistent(ctx, primary_shadow_kernel<true>, a, (size_t)0, nullptr, counter, zero_bytes)
                              : launch_persistent(ctx, primary_shadow_kernel<false>, a, (size_t)0, nullptr, counter, zero_bytes);
     commit_hints(hs, rc);
     return rc;
@@ -1244,10 +1245,10 @@ extern "C" int rt_shadow_device(rt_context* ctx, int64_t n, const rt_ray* d_rays
     a.rays_out = (float4*)d_shadow_rays_out;
     const int st = smem_top_count(ctx);
     if (ctx->opt_scheduler == 1 && !st)
-        rc = launch_lanes(ctx, trace_lanes_kernel<SRC_SHADOW, true>, a, n);
+        rc = (big_scene_instances(ctx) ? launch_lanes(ctx, trace_lanes_kernel<SRC_SHADOW, true, true>, a, n) : launch_lanes(ctx, trace_lanes_kernel<SRC_SHADOW, true>, a, n));
     else
         rc = st ? launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, true>, a, st)
-                : inner_exit_for(ctx) ? launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, false, false, true>, a, 0)
+                : big_scene_instances(ctx) ? launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, false, false, true>, a, 0)
                                       : launch_persistent(ctx, trace_kernel<SRC_SHADOW, true, false>, a, 0);
     return rc;
 }
@@ -1305,7 +1306,7 @@ static int render_frame_impl(rt_context* ctx, int w, int h, int part, int n_part
     rt_context::HintSlot* hs = nullptr;
     if ((rc = attach_hints(ctx, HINT_KIND_FRAME, a, slot, stream, &hs, &counter, &zero_bytes))) return rc;
     rc = st ? launch_persistent(ctx, render_kernel<true>, a, st, stream, counter, zero_bytes)
-            : inner_exit_for(ctx) ? launch_persistent(ctx, render_kernel<false, true>, a, 0, stream, counter, zero_bytes)
+            : big_scene_instances(ctx) ? launch_persistent(ctx, render_kernel<false, true>, a, 0, stream, counter, zero_bytes)
                                   : launch_persistent(ctx, render_kernel<false>, a, 0, stream, counter, zero_bytes);
     commit_hints(hs, rc);
     return rc;

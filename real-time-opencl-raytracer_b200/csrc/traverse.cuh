@@ -50,7 +50,7 @@ struct TraceResult {
 // A scheduling policy only -- every lane's own sequence of visits and tests is unchanged, results are identical. It pays when
 // node fetches are slow (a scene that does not fit L2: stragglers hold the warp for a DRAM round trip per visit; C4 primary
 // 0.357 -> 0.329 ms, shadow 0.553 -> 0.504, frame 1.37 -> 1.27) and costs 2-10 % when they are not (C2), so the host picks
-// the instance per scene (rtb200.cu inner_exit_for).
+// the instance per scene (rtb200.cu big_scene_instances).
 static constexpr int kInnerExitLanes = 8;
 template <bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX, bool ALL_HOISTED, bool INNER_EXIT>
 __device__ __forceinline__ TraceResult traverse_impl(const SceneView& s, const float4* __restrict__ smem_pairs, int smem_count,
