@@ -261,14 +261,20 @@ struct TileWork {
 // s_sched (shared, per block): [0] split entries [1] heavy entries [2] heavy threshold [3] split threshold [4] keep threshold
 // [5] SM clock at block start [6] light entries [7] light threshold
 __device__ __forceinline__ void sched_init(const TraceArgs& a, unsigned int* s_sched) {
+    // The histogram is fetched by the whole block at once (one load per thread) and walked in shared memory, instead of
+    // ~110 dependent global loads by one thread (each step decides whether the next is needed) ahead of the first tile.
+    __shared__ unsigned int s_hist[kHintBins];
+    if (a.hint_in)
+        for (int i = threadIdx.x; i < kHintBins; i += blockDim.x) s_hist[i] = __ldg(a.hint_in + kHintHist + i);
+    __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int n_split = 0, n_heavy = 0, n_light = 0, thr_h = 0xffffffffu, thr_s = 0xffffffffu, thr_k = 0xffffffffu, thr_l = 0u;
         if (a.hint_in) {
-            n_split = min(a.hint_in[0], (unsigned int)(4 * a.num_batches));
-            n_heavy = min(a.hint_in[1], (unsigned int)a.num_batches);
-            n_light = min(a.hint_in[4], (unsigned int)a.num_batches);
-            const unsigned long long span = a.hint_in[3];
-            const unsigned int tiles = a.hint_in[2];
+            n_split = min(__ldg(a.hint_in + 0), (unsigned int)(4 * a.num_batches));
+            n_heavy = min(__ldg(a.hint_in + 1), (unsigned int)a.num_batches);
+            n_light = min(__ldg(a.hint_in + 4), (unsigned int)a.num_batches);
+            const unsigned long long span = __ldg(a.hint_in + 3);
+            const unsigned int tiles = __ldg(a.hint_in + 2);
             if (span && tiles) {
                 auto pct = [&](int p) { const unsigned long long v = span * (unsigned long long)p / 100ull; return v > 0xfffffffeull ? 0xfffffffeu : (unsigned int)v; };
                 thr_s = pct(a.hint_split_pct);
@@ -278,7 +284,7 @@ __device__ __forceinline__ void sched_init(const TraceArgs& a, unsigned int* s_s
                 unsigned long long seen = 0;
                 int bin = kHintBins - 1;
                 for (; bin > 0; bin--) {
-                    seen += a.hint_in[kHintHist + bin];
+                    seen += s_hist[bin];
                     if (seen >= want) break;
                 }
                 thr_h = (unsigned int)bin << kHintBinShift;
@@ -288,7 +294,7 @@ __device__ __forceinline__ void sched_init(const TraceArgs& a, unsigned int* s_s
                 unsigned long long seen_l = 0;
                 int lb = 1;
                 for (; lb < bin; lb++) {
-                    seen_l += a.hint_in[kHintHist + lb];
+                    seen_l += s_hist[lb];
                     if (seen_l > want_l) break;
                 }
                 thr_l = a.hint_light_pct > 0 ? (unsigned int)lb << kHintBinShift : 0u;
