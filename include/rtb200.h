@@ -66,6 +66,11 @@ typedef struct { float ox, oy, oz, tmax, dx, dy, dz, reserved; } rt_ray;
 /* One result, 16 bytes: idx = 3 * triangle id or -1; t = final *tHit; u,v = barycentrics of the
  * accepted triangle (weights of its 2nd and 3rd vertex), 0 when idx < 0. */
 typedef struct { int32_t idx; float t, u, v; } rt_hit;
+/* Alignment: DEVICE buffers of rt_ray / rt_hit (every `d_*` argument, and rt_host_register aliases) must be 16-byte
+ * aligned -- the kernels move records as 16-byte vectors -- and frames 4-byte aligned (the int64 count of
+ * rt_diffuse_rays_device 8). cudaMalloc, torch and rt_ipc_alloc all give 256 bytes or better; a buffer carved at an odd
+ * offset is refused with RT_E_INVALID before anything is launched. HOST buffers may have any alignment: a page-locked
+ * one that is suitably aligned is written directly by the kernel, any other goes through a device buffer and a copy. */
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
 int rt_create(int device_ordinal, rt_context** out_ctx);   /* replaces setupCL() */

@@ -425,7 +425,8 @@ extern "C" int rt_group_set_params(rt_group* g, const float params[32]) {
 static bool zero_copy_target(rt_group* g, void* host, void** alias) {
     cudaPointerAttributes attr;
     memset(&attr, 0, sizeof attr);
-    if (cudaPointerGetAttributes(&attr, host) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+    if (((uintptr_t)host & 3u) ||  // frame words are stored as 4-byte words: an odd destination goes through the copy instead
+        cudaPointerGetAttributes(&attr, host) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
         cudaGetLastError();
         return false;
     }

@@ -828,6 +828,16 @@ static void* pinned_alias(const void* host_ptr) {
     return nullptr;
 }
 
+// rt_ray / rt_hit buffers are read and written as 16-byte vectors and frames as 4-byte words, although the C structs only
+// promise 4-byte alignment: a buffer carved at an odd offset would fault inside the kernel (a sticky CUDA error that takes
+// the whole process' CUDA context with it), so it is refused on the host. nullptr (an optional buffer) passes.
+static bool misaligned(const void* p, unsigned bytes) { return ((uintptr_t)p & (uintptr_t)(bytes - 1)) != 0; }
+#define NEED_ALIGNED(ctx, who, ptr, bytes)                                                                                  \
+    do {                                                                                                                    \
+        if (misaligned((ptr), (bytes)))                                                                                     \
+            return set_err((ctx), RT_E_INVALID, "%s: %s = %p is not %d-byte aligned", (who), #ptr, (const void*)(ptr), (int)(bytes)); \
+    } while (0)
+
 static int smem_top_count(const rt_context* ctx) {
     int c = ctx->opt_smem_top;
     if (c > ctx->hdr.top_pairs) c = ctx->hdr.top_pairs;
@@ -879,6 +889,8 @@ static int band_setup(rt_context* ctx, TraceArgs& a, int w, int h, int part, int
 }
 
 static int do_trace_device(rt_context* ctx, int mode, long long n, const rt_ray* d_rays, rt_hit* d_hits) {
+    NEED_ALIGNED(ctx, "trace", d_rays, 16);
+    NEED_ALIGNED(ctx, "trace", d_hits, 16);
     TraceArgs a;
     memset(&a, 0, sizeof a);
     a.scene = ctx->view;
@@ -911,6 +923,8 @@ extern "C" int rt_trace_sorted_device(rt_context* ctx, int mode, int64_t n, cons
     if (rc) return rc;
     if ((mode != RT_CLOSEST && mode != RT_ANY) || n < 0 || n > 0x7fffffff || (n > 0 && (!d_rays || !d_hits)))
         return set_err(ctx, RT_E_INVALID, "rt_trace_sorted_device: bad arguments");
+    NEED_ALIGNED(ctx, "rt_trace_sorted_device", d_rays, 16);
+    NEED_ALIGNED(ctx, "rt_trace_sorted_device", d_hits, 16);
     ON_DEVICE(ctx);
     if (n == 0) return RT_OK;
     const size_t N = (size_t)n, npad = (N + 63) & ~(size_t)63;
@@ -966,7 +980,8 @@ extern "C" int rt_trace(rt_context* ctx, int mode, int64_t n, const rt_ray* rays
     if (n == 0) return RT_OK;
     ON_DEVICE(ctx);
     if ((rc = ensure(ctx, &ctx->d_stage_in, &ctx->stage_in_bytes, (size_t)n * sizeof(rt_ray)))) return rc;
-    rt_hit* direct_out = ctx->opt_zero_copy ? (rt_hit*)pinned_alias(hits_host) : nullptr;
+    // host buffers are only copied from / to (any alignment will do) unless the kernel stores into them directly
+    rt_hit* direct_out = ctx->opt_zero_copy && !misaligned(hits_host, 16) ? (rt_hit*)pinned_alias(hits_host) : nullptr;
     if (!direct_out && (rc = ensure(ctx, &ctx->d_stage_out, &ctx->stage_out_bytes, (size_t)n * sizeof(rt_hit)))) return rc;
     const int64_t chunk_rays = 1 << 18;  // 8 MB of rays per chunk
     int chunks = (int)((n + chunk_rays - 1) / chunk_rays);
@@ -1018,6 +1033,9 @@ static int primary_impl(rt_context* ctx, int w, int h, int part, int n_parts, in
     int rc = require(ctx, true, false);
     if (rc) return rc;
     if (!d_hits && !d_idx_frame) return set_err(ctx, RT_E_INVALID, "primary pass: no output buffer given");
+    NEED_ALIGNED(ctx, "primary pass", d_hits, 16);
+    NEED_ALIGNED(ctx, "primary pass", d_rays_out, 16);
+    NEED_ALIGNED(ctx, "primary pass", d_idx_frame, 4);
     ON_DEVICE(ctx);
     TraceArgs a;
     memset(&a, 0, sizeof a);
@@ -1051,6 +1069,9 @@ static int primary_shadow_impl(rt_context* ctx, int w, int h, int part, int n_pa
     int rc = require(ctx, true, false);
     if (rc) return rc;
     if (!d_hits && !d_shadow_hits && !d_vis_frame) return set_err(ctx, RT_E_INVALID, "primary+shadow pass: no output buffer given");
+    NEED_ALIGNED(ctx, "primary+shadow pass", d_hits, 16);
+    NEED_ALIGNED(ctx, "primary+shadow pass", d_shadow_hits, 16);
+    NEED_ALIGNED(ctx, "primary+shadow pass", d_vis_frame, 4);
     ON_DEVICE(ctx);
     TraceArgs a;
     memset(&a, 0, sizeof a);
@@ -1084,7 +1105,7 @@ extern "C" int rt_primary_shadow(rt_context* ctx, int w, int h, int32_t* vis_hos
     if (!vis_host || w <= 0 || h <= 0) return set_err(ctx, RT_E_INVALID, "rt_primary_shadow: bad arguments");
     ON_DEVICE(ctx);
     const size_t bytes = (size_t)w * h * 4;
-    void* alias = ctx->opt_zero_copy ? pinned_alias(vis_host) : nullptr;
+    void* alias = ctx->opt_zero_copy && !misaligned(vis_host, 4) ? pinned_alias(vis_host) : nullptr;
     if (alias) {
         if ((rc = primary_shadow_impl(ctx, w, h, 0, 1, 4, nullptr, nullptr, (int32_t*)alias))) return rc;
     } else {
@@ -1197,7 +1218,7 @@ extern "C" int rt_primary(rt_context* ctx, int w, int h, rt_hit* hits_host) {
     const size_t bytes = (size_t)w * h * sizeof(rt_hit);
     // Pinned (page-locked) destination: let the kernel store the hit records straight into host memory over
     // PCIe (zero copy) -- the transfer then overlaps the tracing completely and no staging copy exists.
-    if (ctx->opt_zero_copy) {
+    if (ctx->opt_zero_copy && !misaligned(hits_host, 16)) {
         if (void* alias = pinned_alias(hits_host)) {
             if ((rc = rt_primary_device(ctx, w, h, 0, 1, 4, (rt_hit*)alias, nullptr))) return rc;
             CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1232,6 +1253,10 @@ extern "C" int rt_shadow_device(rt_context* ctx, int64_t n, const rt_ray* d_rays
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!d_rays || !d_hits || !d_shadow_hits))) return set_err(ctx, RT_E_INVALID, "rt_shadow_device: bad arguments");
     if (n == 0) return RT_OK;
+    NEED_ALIGNED(ctx, "rt_shadow_device", d_rays, 16);
+    NEED_ALIGNED(ctx, "rt_shadow_device", d_hits, 16);
+    NEED_ALIGNED(ctx, "rt_shadow_device", d_shadow_hits, 16);
+    NEED_ALIGNED(ctx, "rt_shadow_device", d_shadow_rays_out, 16);
     ON_DEVICE(ctx);
     TraceArgs a;
     memset(&a, 0, sizeof a);
@@ -1259,6 +1284,10 @@ extern "C" int rt_diffuse_rays_device(rt_context* ctx, int64_t n, const rt_ray* 
     if (rc) return rc;
     if (n <= 0 || n > 0x7fffffff || !d_rays || !d_hits || spp < 1 || !d_out_rays)
         return set_err(ctx, RT_E_INVALID, "rt_diffuse_rays_device: bad arguments");
+    NEED_ALIGNED(ctx, "rt_diffuse_rays_device", d_rays, 16);
+    NEED_ALIGNED(ctx, "rt_diffuse_rays_device", d_hits, 16);
+    NEED_ALIGNED(ctx, "rt_diffuse_rays_device", d_out_rays, 16);
+    NEED_ALIGNED(ctx, "rt_diffuse_rays_device", d_count, 8);
     ON_DEVICE(ctx);
     if (ctx->flags_count < (size_t)n) {
         cudaFree(ctx->d_flags);
@@ -1291,6 +1320,7 @@ static int render_frame_impl(rt_context* ctx, int w, int h, int part, int n_part
     int rc = require(ctx, true, true);
     if (rc) return rc;
     if (!d_out) return set_err(ctx, RT_E_INVALID, "rt_render_frame_device: d_out is NULL");
+    NEED_ALIGNED(ctx, "rt_render_frame_device", d_out, 4);
     ON_DEVICE(ctx);
     TraceArgs a;
     memset(&a, 0, sizeof a);
@@ -1322,7 +1352,7 @@ extern "C" int rt_render_frame(rt_context* ctx, int w, int h, uint32_t* out_host
     if (!out_host || w <= 0 || h <= 0) return set_err(ctx, RT_E_INVALID, "rt_render_frame: bad arguments");
     ON_DEVICE(ctx);
     const size_t bytes = (size_t)w * h * 4;
-    void* alias = ctx->opt_zero_copy ? pinned_alias(out_host) : nullptr;
+    void* alias = ctx->opt_zero_copy && !misaligned(out_host, 4) ? pinned_alias(out_host) : nullptr;
     if (alias) {  // pinned destination: the kernel stores the pixels straight into host memory
         if ((rc = rt_render_frame_device(ctx, w, h, 0, 1, 4, (uint32_t*)alias))) return rc;
     } else {
@@ -1354,7 +1384,7 @@ extern "C" int rt_render_frame_begin(rt_context* ctx, int w, int h, uint32_t* ou
         CK(ctx, cudaEventRecord(sl.start, ctx->stream));
         CK(ctx, cudaStreamWaitEvent(sl.stream, sl.start, 0));
     }
-    void* alias = ctx->opt_zero_copy ? pinned_alias(out_host) : nullptr;
+    void* alias = ctx->opt_zero_copy && !misaligned(out_host, 4) ? pinned_alias(out_host) : nullptr;
     if (alias) {
         if ((rc = render_frame_impl(ctx, w, h, 0, 1, 4, (uint32_t*)alias, own ? slot : -1))) return rc;
         sl.host = nullptr;
