@@ -271,6 +271,9 @@ int rt_cull_rect_host(const float params[32], int w, int h, int64_t out_x0_x1_y0
 /* Option "inner_exit_batch" (-1 auto / 0 / 1): which instance of the batch kernels' traversal loop runs -- with 1 a warp
  * leaves the inner-node loop as soon as fewer than 8 of its lanes still descend while others wait on a leaf. Same results;
  * auto picks it when the scene's node pairs + triangles do not fit the L2 cache (measured: +8-10 % there, -2-10 % otherwise). */
+/* Option "l2_warm" (default 0; 1 node pairs + triangles, 2 pairs, 3 triangles; "l2_warm_chunk_kb", 16): every traversal
+ * launch first asks L2 for the scene's traversal data with bulk prefetches. An experiment kept for measurement: launches that
+ * find L2 flushed are only 1-2.5 % slower than warm ones and the warm-up costs more than that (profiles/r2_experiments.md 14). */
 /* GPU self test of the box test's hoisted exact division against the compiler's IEEE division on
  * `samples` random operand pairs; *out_mismatches must come back 0. */
 int rt_selftest(rt_context* ctx, int64_t samples, uint32_t seed, uint64_t* out_mismatches);

@@ -64,6 +64,11 @@ struct TraceArgs {
     unsigned int* hint_out;
     int hint_heavy_pct, hint_light_pct;   // the slowest / quickest N percent of the tiles that traced
     int hint_split_pct, hint_keep_pct;    // percent of the previous launch's span
+    // L2 warm-up (option "l2_warm"): the first thread of every block asks L2 for its share of [warm_base, + warm_bytes)
+    // -- node pairs and packed triangles, contiguous in the blob -- before it starts tracing. 0 bytes = off.
+    const char* warm_base;
+    unsigned long long warm_bytes;
+    unsigned int warm_chunk;  // bytes per bulk prefetch, a multiple of 16
 #ifdef RTB_TIMELINE
     unsigned long long* timeline;  // tools build only: {start ns, end ns | smid << 56} per batch (tools/timeline_probe.py)
 #endif
@@ -181,6 +186,19 @@ __device__ __forceinline__ void tile_pixel(const TraceArgs& a, long long batch, 
     int tx;
     long long k;
     tile_pixel(a, batch, lane, x, y, tx, k);
+}
+
+// L2 warm-up: cp.async.bulk.prefetch.L2 moves a whole chunk DRAM -> L2 with one instruction and no register or shared-memory
+// destination. A launch that finds L2 cold (another working set went through it since the last frame) otherwise pays one
+// DRAM round trip per first touch of a node or a triangle, inside the dependent chain of a traversal.
+__device__ __forceinline__ void warm_l2(const TraceArgs& a) {
+    if (!a.warm_bytes || threadIdx.x != 0) return;
+    const unsigned long long chunk = a.warm_chunk;
+    for (unsigned long long off = (unsigned long long)blockIdx.x * chunk; off < a.warm_bytes; off += (unsigned long long)gridDim.x * chunk) {
+        const unsigned long long left = a.warm_bytes - off;
+        const unsigned int n = (unsigned int)(left < chunk ? left : chunk);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.warm_base + off), "r"(n) : "memory");
+    }
 }
 
 // RT_CNT_RAYS_TRACED: every lane counts the traversals it starts; one warp reduction + atomicAdd when the warp retires.
@@ -482,6 +500,7 @@ __global__ void __launch_bounds__(kBlockThreads, (SRC == SRC_PRIMARY && !FAST_BO
     const int lane = threadIdx.x & 31;
     unsigned int traced = 0;
     __shared__ unsigned int s_sched[8];
+    warm_l2(a);
     if (SRC == SRC_PRIMARY) sched_init(a, s_sched);
     unsigned int ahead = 0;
     if (SRC == SRC_PRIMARY && kQueuePrefetch && a.hint_out && lane == 0) ahead = queue_fetch(a);
@@ -585,6 +604,7 @@ __global__ void __launch_bounds__(kBlockThreads) primary_shadow_kernel(const Tra
     const f3 light_pos = ld3(a.params.light_pos);
     unsigned int traced = 0;
     __shared__ unsigned int s_sched[8];
+    warm_l2(a);
     sched_init(a, s_sched);
     unsigned int ahead = 0;
     if (kQueuePrefetch && a.hint_out && lane == 0) ahead = queue_fetch(a);
@@ -783,6 +803,7 @@ __global__ void __launch_bounds__(kBlockThreads, 8) render_kernel(const TraceArg
     const int lane = threadIdx.x & 31;
     unsigned int traced = 0;
     __shared__ unsigned int s_sched[8];
+    warm_l2(a);
     sched_init(a, s_sched);
     unsigned int ahead = 0;  // no fetch-ahead here: the extra live register costs this kernel 120 bytes of spills
     for (;;) {

@@ -24,6 +24,7 @@ template <int SRC, bool ANY_HIT, bool WIDE_L2 = false>
 __global__ void __launch_bounds__(kBlockThreads, RTB_MINB_LANES) trace_lanes_kernel(const TraceArgs a, int refill_threshold, int inner_exit_threshold) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    warm_l2(a);
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned long long total = (SRC == SRC_PRIMARY) ? (unsigned long long)a.num_batches * 32ull : (unsigned long long)a.n;
 

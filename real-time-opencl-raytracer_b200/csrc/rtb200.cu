@@ -79,6 +79,9 @@ struct rt_context {
     int opt_overlap_frames = 1; // rt_render_frame_begin: one-kernel frames on per-slot streams (frames in flight overlap)
     int opt_store_group = -1;   // row assembly of 4-byte/pixel frames: -1 = auto (on when the frame is host or peer memory),
                                 // 0 = off, 2 = groups of 4 tiles (128-byte rows), 4 = groups of 16 tiles (512-byte rows)
+    int opt_l2_warm = 0;        // bulk L2 prefetch of node pairs + packed triangles at the start of every traversal launch:
+                                // 0 off, 1 pairs + triangles, 2 pairs only, 3 triangles only (kernels.cuh warm_l2)
+    int opt_l2_warm_chunk_kb = 16;
     int opt_l2_persist_kb = 0;  // experiment: L2 persisting access window over the first N KB of the node pairs (the BFS-ordered top)
     int opt_batch_inner_exit = -1;  // batch kernels: early exit from the inner loop (traverse.cuh INNER_EXIT): -1 = when the scene's
                                 // traversal data (node pairs + triangles) does not fit L2, 0 = never, 1 = always
@@ -436,6 +439,8 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
         if (ctx->have_scene) ctx->view.coords_in_window = ctx->opt_exact_div ? 0 : ctx->hdr.coords_in_window;
     } else if (!strcmp(name, "overlap_frames")) ctx->opt_overlap_frames = value ? 1 : 0;
     else if (!strcmp(name, "store_group")) ctx->opt_store_group = (value == 0 || value == 2 || value == 4) ? value : -1;
+    else if (!strcmp(name, "l2_warm")) ctx->opt_l2_warm = (value >= 0 && value <= 3) ? value : 0;
+    else if (!strcmp(name, "l2_warm_chunk_kb")) ctx->opt_l2_warm_chunk_kb = value < 1 ? 1 : (value > 1024 ? 1024 : value);
     else if (!strcmp(name, "l2_persist_kb")) { ctx->opt_l2_persist_kb = value < 0 ? 0 : value; return apply_l2_window(ctx); }
     else if (!strcmp(name, "gate_cull")) ctx->opt_gate_cull = value ? 1 : 0;
     else if (!strcmp(name, "inner_exit_batch")) ctx->opt_batch_inner_exit = value < 0 ? -1 : (value ? 1 : 0);
@@ -533,6 +538,22 @@ static int blocks_per_sm(rt_context* ctx, K kernel, size_t smem, int* out) {
     return RT_OK;
 }
 
+static void warm_setup(const rt_context* ctx, TraceArgs& a) {
+    a.warm_base = nullptr;
+    a.warm_bytes = 0;
+    a.warm_chunk = (unsigned int)ctx->opt_l2_warm_chunk_kb * 1024u;
+    if (!ctx->opt_l2_warm) return;
+    const unsigned long long pairs_bytes = ctx->hdr.off_tris - ctx->hdr.off_pairs, tris_bytes = ctx->hdr.off_verts - ctx->hdr.off_tris;
+    const char* pairs = (const char*)ctx->view.pairs;
+    if (ctx->opt_l2_warm == 3) {
+        a.warm_base = pairs + pairs_bytes;
+        a.warm_bytes = tris_bytes;
+    } else {
+        a.warm_base = pairs;
+        a.warm_bytes = ctx->opt_l2_warm == 2 ? pairs_bytes : pairs_bytes + tris_bytes;
+    }
+}
+
 template <typename K, typename... Extra>
 static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, size_t smem, cudaStream_t stream, unsigned long long* counter,
                              size_t zero_bytes, Extra... extra) {
@@ -553,6 +574,7 @@ static int launch_persistent(rt_context* ctx, K kernel, TraceArgs& a, size_t sme
     if (blocks < 1) return RT_OK;  // nothing to do
     a.work_counter = counter;
     a.ray_counter = ctx->d_counter + kRayCounterSlot;
+    warm_setup(ctx, a);
 #ifdef RTB_TIMELINE
     a.timeline = ctx->d_timeline;
 #endif
@@ -811,6 +833,7 @@ static int launch_lanes(rt_context* ctx, K kernel, TraceArgs& a, long long total
     if (blocks < 1) return RT_OK;
     a.work_counter = ctx->d_counter;
     a.ray_counter = ctx->d_counter + kRayCounterSlot;
+    warm_setup(ctx, a);
     CK(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
     kernel<<<(unsigned)blocks, kBlockThreads, 0, ctx->stream>>>(a, ctx->opt_refill, ctx->opt_inner_exit);
     CK(ctx, cudaGetLastError());
