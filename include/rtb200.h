@@ -274,6 +274,8 @@ int rt_cull_rect_host(const float params[32], int w, int h, int64_t out_x0_x1_y0
 /* Option "l2_warm" (default 0; 1 node pairs + triangles, 2 pairs, 3 triangles; "l2_warm_chunk_kb", 16): every traversal
  * launch first asks L2 for the scene's traversal data with bulk prefetches. An experiment kept for measurement: launches that
  * find L2 flushed are only 1-2.5 % slower than warm ones and the warm-up costs more than that (profiles/r2_experiments.md 14). */
+/* Option "smem_carveout" (-1 = the driver's choice; 0..100 = cudaFuncAttributePreferredSharedMemoryCarveout of the traversal
+ * kernels): an experiment kept for measurement -- the default split is within noise of the best (r2_experiments.md 15). */
 /* GPU self test of the box test's hoisted exact division against the compiler's IEEE division on
  * `samples` random operand pairs; *out_mismatches must come back 0. */
 int rt_selftest(rt_context* ctx, int64_t samples, uint32_t seed, uint64_t* out_mismatches);

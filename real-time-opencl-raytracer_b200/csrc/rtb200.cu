@@ -82,6 +82,8 @@ struct rt_context {
     int opt_l2_warm = 0;        // bulk L2 prefetch of node pairs + packed triangles at the start of every traversal launch:
                                 // 0 off, 1 pairs + triangles, 2 pairs only, 3 triangles only (kernels.cuh warm_l2)
     int opt_l2_warm_chunk_kb = 16;
+    int opt_smem_carveout = -1;  // experiment: cudaFuncAttributePreferredSharedMemoryCarveout of the traversal kernels (percent of the
+    bool carveout_touched = false;  // L1/shared array given to shared memory; -1 = the driver's choice, 0 = largest L1)
     int opt_l2_persist_kb = 0;  // experiment: L2 persisting access window over the first N KB of the node pairs (the BFS-ordered top)
     int opt_batch_inner_exit = -1;  // batch kernels: early exit from the inner loop (traverse.cuh INNER_EXIT): -1 = when the scene's
                                 // traversal data (node pairs + triangles) does not fit L2, 0 = never, 1 = always
@@ -439,6 +441,11 @@ extern "C" int rt_set_option(rt_context* ctx, const char* name, int value) {
         if (ctx->have_scene) ctx->view.coords_in_window = ctx->opt_exact_div ? 0 : ctx->hdr.coords_in_window;
     } else if (!strcmp(name, "overlap_frames")) ctx->opt_overlap_frames = value ? 1 : 0;
     else if (!strcmp(name, "store_group")) ctx->opt_store_group = (value == 0 || value == 2 || value == 4) ? value : -1;
+    else if (!strcmp(name, "smem_carveout")) {
+        ctx->opt_smem_carveout = value < 0 ? -1 : (value > 100 ? 100 : value);
+        ctx->carveout_touched = true;
+        ctx->occ_count = 0;  // re-applied at each kernel's next launch
+    }
     else if (!strcmp(name, "l2_warm")) ctx->opt_l2_warm = (value >= 0 && value <= 3) ? value : 0;
     else if (!strcmp(name, "l2_warm_chunk_kb")) ctx->opt_l2_warm_chunk_kb = value < 1 ? 1 : (value > 1024 ? 1024 : value);
     else if (!strcmp(name, "l2_persist_kb")) { ctx->opt_l2_persist_kb = value < 0 ? 0 : value; return apply_l2_window(ctx); }
@@ -530,6 +537,7 @@ static int blocks_per_sm(rt_context* ctx, K kernel, size_t smem, int* out) {
             return RT_OK;
         }
     if (smem > 48 * 1024) CK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ctx->carveout_touched) CK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->opt_smem_carveout));
     int per_sm = 1;
     CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, smem));
     if (per_sm < 1) per_sm = 1;
