@@ -52,12 +52,30 @@ struct TraceResult {
 // 0.357 -> 0.329 ms, shadow 0.553 -> 0.504, frame 1.37 -> 1.27) and costs 2-10 % when they are not (C2), so the host picks
 // the instance per scene (rtb200.cu big_scene_instances).
 static constexpr int kInnerExitLanes = 8;
+#ifdef RTB_SMEM_STACK
+// one array per kernel, shared by every instance of the loop inlined into it (a thread runs them one after the other)
+__device__ __forceinline__ int* smem_stack_base() {
+    __shared__ int s_stack[RTB_SMEM_STACK * RTB_BLOCK_THREADS];
+    return s_stack;
+}
+#endif
 template <bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX, bool ALL_HOISTED, bool INNER_EXIT>
 __device__ __forceinline__ TraceResult traverse_impl(const SceneView& s, const float4* __restrict__ smem_pairs, int smem_count,
                                                      const Ray& ray, const RayX& rx, float tHit) {
     RayF rf;
     if (FAST_BOX) rf = ray_fast_prepare(ray);
+#ifdef RTB_SMEM_STACK
+    // experiment (VERDICT r1 task 7): the first RTB_SMEM_STACK postponed nodes of every thread live in shared memory
+    // (entry-major, so a warp's accesses to one depth are conflict-free), deeper ones in local memory as before
+    int* const my_stack = smem_stack_base() + threadIdx.x;
+    int stack[RTB_STACK - RTB_SMEM_STACK];
+#define RTB_PUSH(v) do { if (sp < RTB_SMEM_STACK) my_stack[sp * RTB_BLOCK_THREADS] = (v); else stack[sp - RTB_SMEM_STACK] = (v); sp++; } while (0)
+#define RTB_POP() (--sp, sp < RTB_SMEM_STACK ? my_stack[sp * RTB_BLOCK_THREADS] : stack[sp - RTB_SMEM_STACK])
+#else
     int stack[RTB_STACK];
+#define RTB_PUSH(v) (stack[sp++] = (v))
+#define RTB_POP() (stack[--sp])
+#endif
     int sp = 0;
     int cur = s.root_ref;
     TraceResult res;
@@ -95,7 +113,7 @@ __device__ __forceinline__ TraceResult traverse_impl(const SceneView& s, const f
             if (hit0 && hit1) {
                 if (t0n > t1n) { const int t = c0; c0 = c1; c1 = t; }
                 if (sp >= RTB_STACK) { res.idx = -1; res.t = tHit; res.u = res.v = 0.0f; return res; }
-                stack[sp++] = c1;
+                RTB_PUSH(c1);
                 cur = c0;
 #ifdef RTB_PREFETCH_FAR
                 // experiment: the postponed child will be popped later -- pull its node pair / first triangle towards L2 now
@@ -110,7 +128,7 @@ __device__ __forceinline__ TraceResult traverse_impl(const SceneView& s, const f
                 cur = c1;
             } else {
                 if (sp == 0) { res.t = tHit; return res; }
-                cur = stack[--sp];
+                cur = RTB_POP();
             }
             if (INNER_EXIT) {
                 const int still = __popc(__ballot_sync(__activemask(), cur >= 0));
@@ -161,8 +179,10 @@ __device__ __forceinline__ TraceResult traverse_impl(const SceneView& s, const f
 #endif
         }
         if (sp == 0) { res.t = tHit; return res; }
-        cur = stack[--sp];
+        cur = RTB_POP();
     }
+#undef RTB_PUSH
+#undef RTB_POP
 }
 
 template <bool ANY_HIT, bool SMEM_TOP, bool FAST_BOX = false, bool INNER_EXIT = false>
