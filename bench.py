@@ -160,8 +160,9 @@ def oracle_pass(arrays, bvh, params, w, h, repeats, threads=None):
     """CPU restatement of the reference kernel (oracle/) on the same frame: seconds per pass + visit counts."""
     from oracle import oracle_py as O
 
-    if threads:
-        O.lib().orc_set_num_threads(threads)
+    if threads is None:  # every core this process may run on; torchrun exports OMP_NUM_THREADS=1, which would leave one
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    O.lib().orc_set_num_threads(threads)
     sc = O.OracleScene(arrays, bvh.nodes, bvh.tri_indices)
     rays, gate = O.primary_rays(params, w, h)
     live = np.ascontiguousarray(rays[gate.astype(bool)])
