@@ -258,6 +258,32 @@ def test_group_frames_equal_single_context(ctx, pinned):
             grp.close()
 
 
+def test_group_host_frame_at_an_odd_offset(ctx):
+    """a page-locked frame the kernels cannot store words into (2 bytes off) goes through the gather frame + copy"""
+    import torch
+
+    g = load_scene("mix")
+    _upload(ctx, g)
+    w, h = 200, 120
+    params, _ = rtb200.camera_params(w, h, g["aabb_min"], g["aabb_max"])
+    ctx.set_params(params)
+    want = ctx.render_frame(w, h)
+    for n in _group_sizes():
+        grp = rtb200.Group(n)
+        try:
+            grp.upload_scene(mesh_dict(g), g["ref_nodes"], g["ref_tri_indices"])
+            grp.set_params(params)
+            store = torch.zeros(4 * w * h + 16, dtype=torch.uint8).pin_memory()
+            raw = store.numpy()
+            fr = np.frombuffer(raw.data, dtype=np.uint32, count=w * h, offset=2).reshape(h, w)
+            grp.render_frame(w, h, fr)
+            assert np.array_equal(fr, want), f"{n} GPUs"
+            assert grp.stats()["zero_copy"] == 0.0
+            assert (raw[:2] == 0).all() and (raw[2 + 4 * w * h:] == 0).all()
+        finally:
+            grp.close()
+
+
 def test_group_errors():
     import torch
 
